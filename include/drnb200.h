@@ -1,0 +1,156 @@
+/*
+ * drnb200.h — C ABI of libdrnb200.so: the B200 (sm_100a) inference path for block-pruned DRN
+ * semantic segmentation.
+ *
+ * The reference (thejasvi-konduru/video-seg-model-compress) is pure Python/PyTorch and defines no
+ * FFI of its own; the boundary it exposes for this path is two Python interfaces, `DRNSeg.forward`
+ * (semantic_seg.py:126-164) and `Pruner.mask_dict` (pruners/Pruner.py:6-27).  The host-side mirror of
+ * those interfaces (video-seg-model-compress_b200/drnb200/) binds exactly the entry points below with
+ * ctypes; each one names the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative DRNB200_E_* code otherwise; it never throws.
+ *     drnb200_last_error() returns a thread-local, human readable description of the last failure.
+ *   - all data pointers are DEVICE pointers owned by the caller (the Python host passes
+ *     torch tensors' data_ptr()); the library owns only the opaque plan handles.
+ *   - every launch is enqueued on the cudaStream_t passed as `stream` (a void* so that no CUDA header is
+ *     needed to bind); there are no hidden synchronisations on the forward calls.  Plan creation may
+ *     synchronise (it reads the tile list back to sort the work list).
+ *   - there is NO CPU fallback: without an sm_100 device the calls fail with DRNB200_E_CUDA.
+ *   - 16-bit activation tensors are NHWC; `act_dtype` says whether the 16 bits are bf16 or fp16.
+ */
+#ifndef DRNB200_H_
+#define DRNB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRNB200_VERSION 100
+
+/* error codes */
+#define DRNB200_OK          0
+#define DRNB200_E_ARG      -1   /* bad argument / unsupported shape */
+#define DRNB200_E_CUDA     -2   /* CUDA runtime / driver error */
+#define DRNB200_E_NOMEM    -3
+#define DRNB200_E_STATE    -4   /* plan used in a way it was not built for */
+
+/* 16-bit activation / packed-weight storage type */
+#define DRNB200_BF16 0
+#define DRNB200_F16  1
+
+/* conv implementation selector (drnb200_conv_desc.impl) */
+#define DRNB200_IMPL_AUTO    0   /* tcgen05 when the shape allows it, else CUDA-core direct kernel */
+#define DRNB200_IMPL_DIRECT  1   /* CUDA-core direct convolution (any shape; cross-check path)       */
+#define DRNB200_IMPL_TCGEN05 2   /* tcgen05/TMEM/TMA implicit GEMM; fails if the shape is unsupported */
+
+int         drnb200_version(void);
+const char* drnb200_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a) mask -> block-sparse tile list.
+ * Replaces: nothing executable in the reference at inference time (masks are only multiplied into
+ * dense weights, pruners/Pruner.py:17-20).  The format follows the reference's BSR exporter
+ * BlockPruner.generate_block_matrix (pruners/BlockPruner.py:344-413: indices + rowBlockPtr) and its
+ * liveness rule tools/visualize_layers.py:8-13, re-ordered for an NHWC implicit GEMM:
+ *   the matricised weight (O, I*kh*kw) has column  ci*kh*kw + tap  (BlockPruner.py:144);
+ *   a K-block is  kb = cib * (kh*kw) + tap  with cib = ci / tile_ci;   an output tile is ot = o / tile_o;
+ *   block (ot, kb) is live  <=>  any mask element in it is != 0  (HbPruner masks may exceed 1).
+ * Outputs (device): row_ptr[n_ot+1] (exclusive prefix of live counts), kblk[row_ptr[n_ot]] (live kb ids,
+ * ascending inside each ot), *n_live = row_ptr[n_ot].   kblk must have room for n_ot*n_cib*kh*kw ints.
+ * O % tile_o == 0 and I % tile_ci == 0 are required.
+ * ------------------------------------------------------------------------------------------- */
+int drnb200_compact_mask(const float* mask_oihw, int O, int I, int kh, int kw,
+                         int tile_o, int tile_ci,
+                         int32_t* row_ptr, int32_t* kblk, int32_t* n_live, void* stream);
+
+/* Pack the live blocks of (w * (mask != 0)) as 16-bit K-major tiles in the shared-memory image the
+ * tcgen05 kernels consume: tile j (in kblk order) is tile_o rows x tile_ci elements, row pitch
+ * tile_ci*2 bytes (32/64/128), 16-byte chunks XOR-swizzled exactly as TMA/UMMA SWIZZLE_{32,64,128}B
+ * would lay them out (tile_ci must be 16, 32 or 64; larger Cin is split into 64-wide K-blocks by
+ * choosing tile_ci = 64).  mask may be NULL (use w as is).  Replaces Pruner.apply_masks
+ * (pruners/Pruner.py:17-20) + the `values` array of BlockPruner.generate_block_matrix. */
+int drnb200_pack_weights(const float* w_oihw, const float* mask_oihw_or_null,
+                         int O, int I, int kh, int kw, int tile_o, int tile_ci,
+                         const int32_t* row_ptr, const int32_t* kblk,
+                         int act_dtype, uint16_t* w_packed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (b) convolution + folded BatchNorm (+ residual) (+ ReLU).
+ * Replaces nn.Conv2d -> BatchNorm2d(eval) -> [+= residual] -> ReLU as composed in
+ * drn.py:49-65 (BasicBlock.forward), drn.py:86-106 (Bottleneck.forward), drn.py:201-211
+ * (_make_conv_layers) and drn.py:181-186 (downsample).  padding == dilation*(ksize/2) as everywhere
+ * in drn.py.   y = act( conv(x) * bn_scale[c] + bn_shift[c] (+ residual) ),  fp32 accumulation.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct drnb200_conv_desc {
+  int32_t N, H, W;          /* input batch, height, width                                        */
+  int32_t Cin, Cout;
+  int32_t ksize;            /* 1 or 3                                                            */
+  int32_t stride;           /* 1 or 2                                                            */
+  int32_t dilation;         /* >= 1                                                              */
+  int32_t relu;             /* apply ReLU last                                                   */
+  int32_t has_residual;     /* add `residual` (output-shaped, act_dtype NHWC) before the ReLU    */
+  int32_t act_dtype;        /* DRNB200_BF16 / DRNB200_F16: x, residual, y and packed weights     */
+  int32_t out_f32;          /* write y as float32 NHWC instead of act_dtype (hand-off to the head) */
+  int32_t tile_o, tile_ci;  /* granularity the tile list / packed weights were built with        */
+  int32_t impl;             /* DRNB200_IMPL_*                                                    */
+} drnb200_conv_desc;
+
+typedef struct drnb200_conv_plan drnb200_conv_plan;
+
+int  drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_conv_desc* desc,
+                              const int32_t* row_ptr, const int32_t* kblk, const uint16_t* w_packed,
+                              const float* bn_scale, const float* bn_shift);
+int  drnb200_conv_forward(drnb200_conv_plan* plan, const void* x_nhwc, const void* residual_or_null,
+                          void* y_nhwc, void* stream);
+/* what the plan resolved to: 1 = direct, 2 = tcgen05; number of kernel launches per forward */
+int  drnb200_conv_plan_impl(const drnb200_conv_plan* plan);
+/* live multiply-accumulates of one forward (tile-list granularity) — the numerator of tensor-pipe
+ * utilisation counted at block granularity; element-granularity MACs are computed by the host. */
+int64_t drnb200_conv_plan_tile_macs(const drnb200_conv_plan* plan);
+void drnb200_conv_plan_destroy(drnb200_conv_plan* plan);
+
+/* Stem: nn.Conv2d(3,C0,7,stride 1,pad 3) -> BatchNorm2d -> ReLU (drn.py:132-137).
+ * x: float32 NCHW [N,3,H,W] exactly as the callers feed DRNSeg.forward (semantic_seg.py:444);
+ * w: float32 OIHW [C0,3,7,7]; y: act_dtype NHWC [N,H,W,C0].  C0 must be 16. */
+int drnb200_stem_forward(const float* x_nchw, const float* w_oihw, const float* bn_scale,
+                         const float* bn_shift, int N, int H, int W, int C0, int act_dtype,
+                         void* y_nhwc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (c) fused head: 1x1 classifier `seg` (semantic_seg.py:137-143) -> fixed bilinear grouped
+ * ConvTranspose2d(k16,s8,p4) `up` (semantic_seg.py:115-124,147-152; zero padded borders, analytic
+ * weights w[k] = 1-|2k-15|/16) -> [LogSoftmax, semantic_seg.py:139,158] -> argmax over classes with
+ * first-max tie-break (torch.max(final,1), semantic_seg.py:445).
+ * x: layer-8 output, act_dtype NHWC [N,h,w,C] (C % 16 == 0).  seg_w: float32 [classes, C]
+ * (nn.Conv2d weight [classes,C,1,1]), seg_b: float32 [classes]; both are read once at plan creation
+ * (rounded to act_dtype for the tensor-core classifier GEMM; the bias stays float32).
+ * Any of the forward outputs may be NULL:
+ *   labels      uint8  [N,8h,8w]            (fast path)
+ *   seg_logits  float32 [N,classes,h,w]     (DRNSeg.forward()[1])
+ *   logprob     float32 [N,classes,8h,8w]   (DRNSeg.forward()[0], parity mode only)
+ * classes <= 32.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct drnb200_head_plan drnb200_head_plan;
+
+int  drnb200_head_plan_create(drnb200_head_plan** out, int N, int h, int w, int C, int classes,
+                              int act_dtype, const float* seg_w, const float* seg_b, void* stream);
+int  drnb200_head_forward(drnb200_head_plan* plan, const void* x_nhwc, uint8_t* labels,
+                          float* seg_logits, float* logprob, void* stream);
+void drnb200_head_plan_destroy(drnb200_head_plan* plan);
+
+/* Confusion matrix accumulation: fast_hist (semantic_seg.py:293-296).
+ * hist[label*classes + pred] += 1 for every pixel with 0 <= label < classes (255 = ignore falls out).
+ * pred: uint8; label: uint8 if label_is_i64 == 0 else int64; hist: int64 [classes*classes], accumulates. */
+int drnb200_confusion(const uint8_t* pred, const void* label, int label_is_i64, int64_t n_px,
+                      int classes, int64_t* hist, void* stream);
+
+/* uint8 labels -> int64 (the dtype torch.max returns, semantic_seg.py:445) */
+int drnb200_labels_to_i64(const uint8_t* labels, int64_t n, int64_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRNB200_H_ */

@@ -1,0 +1,391 @@
+// selftest.cu — standalone GPU self-test of libdrnb200.so through its C ABI (no Python, no torch).
+// One case per process invocation (a trapped kernel poisons the context), driven by tools/run_selftest.sh.
+// The CPU loops in here are test scaffolding only; the parity tests proper live in tests/ and use oracle/.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../include/drnb200.h"
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(3);                                                                        \
+    }                                                                                 \
+  } while (0)
+#define API(call)                                                                     \
+  do {                                                                                \
+    int rc_ = (call);                                                                 \
+    if (rc_ != 0) {                                                                   \
+      printf("API error %d (%s) at %s:%d\n", rc_, drnb200_last_error(), __FILE__, __LINE__); \
+      exit(4);                                                                        \
+    }                                                                                 \
+  } while (0)
+
+static uint32_t g_seed = 12345;
+static float frand() {  // uniform in [-1, 1)
+  g_seed = g_seed * 1664525u + 1013904223u;
+  return ((g_seed >> 8) & 0xFFFF) / 32768.0f - 1.0f;
+}
+static uint16_t to16(float f, int dt) {
+  if (dt == DRNB200_BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  return __half_as_ushort(__float2half_rn(f));
+}
+static float from16(uint16_t v, int dt) {
+  if (dt == DRNB200_BF16) return __bfloat162float(__ushort_as_bfloat16(v));
+  return __half2float(__ushort_as_half(v));
+}
+static float round16(float f, int dt) { return from16(to16(f, dt), dt); }
+
+template <class T>
+static T* dev_upload(const std::vector<T>& h) {
+  T* d = nullptr;
+  CK(cudaMalloc(&d, h.size() * sizeof(T) + 16));
+  CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+template <class T>
+static std::vector<T> dev_download(const T* d, size_t n) {
+  std::vector<T> h(n);
+  CK(cudaMemcpy(h.data(), d, n * sizeof(T), cudaMemcpyDeviceToHost));
+  return h;
+}
+
+struct ConvCase {
+  const char* name;
+  int N, H, W, Cin, Cout, k, s, d, relu, res, dt, out_f32, tile_o, tile_ci, impl;
+  float density;   // probability that an (ot, cib) block is live (all taps)
+  int per_tap;     // 1: liveness drawn per (ot, cib, tap)
+  int identity;    // 1: 1x1 identity-like weights (diagnostic)
+  int ref_direct;  // 1: compare against the CUDA-core direct kernel instead of the CPU loops
+};
+
+static void cpu_conv(const ConvCase& c, const std::vector<float>& x, const std::vector<float>& w,
+                     const std::vector<float>& scale, const std::vector<float>& shift,
+                     const std::vector<float>& res, std::vector<float>& y, int OH, int OW) {
+  const int half = c.k / 2;
+  for (int n = 0; n < c.N; ++n)
+    for (int oy = 0; oy < OH; ++oy)
+      for (int ox = 0; ox < OW; ++ox)
+        for (int co = 0; co < c.Cout; ++co) {
+          double acc = 0;
+          for (int ky = 0; ky < c.k; ++ky)
+            for (int kx = 0; kx < c.k; ++kx) {
+              const int iy = oy * c.s + (ky - half) * c.d, ix = ox * c.s + (kx - half) * c.d;
+              if (iy < 0 || iy >= c.H || ix < 0 || ix >= c.W) continue;
+              const float* xp = &x[(((size_t)n * c.H + iy) * c.W + ix) * c.Cin];
+              for (int ci = 0; ci < c.Cin; ++ci)
+                acc += (double)xp[ci] * w[(((size_t)co * c.Cin + ci) * c.k + ky) * c.k + kx];
+            }
+          const size_t off = (((size_t)n * OH + oy) * OW + ox) * c.Cout + co;
+          float v = (float)acc * scale[co] + shift[co];
+          if (c.res) v += res[off];
+          if (c.relu) v = fmaxf(v, 0.f);
+          y[off] = v;
+        }
+}
+
+static int run_conv(const ConvCase& c) {
+  const int taps = c.k * c.k;
+  const int OH = (c.H - 1) / c.s + 1, OW = (c.W - 1) / c.s + 1;
+  const size_t nx = (size_t)c.N * c.H * c.W * c.Cin, ny = (size_t)c.N * OH * OW * c.Cout;
+  const size_t nw = (size_t)c.Cout * c.Cin * taps;
+  const int n_ot = c.Cout / c.tile_o, n_cib = c.Cin / c.tile_ci, n_kb = n_cib * taps;
+  printf("case %s: N=%d HxW=%dx%d Cin=%d Cout=%d k=%d s=%d d=%d relu=%d res=%d dt=%d f32out=%d tile=%dx%d "
+         "impl=%d density=%.2f\n", c.name, c.N, c.H, c.W, c.Cin, c.Cout, c.k, c.s, c.d, c.relu, c.res,
+         c.dt, c.out_f32, c.tile_o, c.tile_ci, c.impl, c.density);
+
+  std::vector<float> xf(nx), wf(nw), mf(nw), scale(c.Cout), shift(c.Cout), resf(ny);
+  std::vector<uint16_t> x16(nx), res16(ny);
+  for (size_t i = 0; i < nx; ++i) { x16[i] = to16(frand(), c.dt); xf[i] = from16(x16[i], c.dt); }
+  for (size_t i = 0; i < ny; ++i) { res16[i] = to16(frand(), c.dt); resf[i] = from16(res16[i], c.dt); }
+  const float wscale = 1.0f / sqrtf((float)c.Cin * taps);
+  // block mask
+  std::vector<uint8_t> live((size_t)n_ot * n_kb, 0);
+  for (int ot = 0; ot < n_ot; ++ot)
+    for (int cib = 0; cib < n_cib; ++cib) {
+      const bool blk = (frand() * 0.5f + 0.5f) < c.density;
+      for (int t = 0; t < taps; ++t) {
+        bool l = blk;
+        if (c.per_tap) l = (frand() * 0.5f + 0.5f) < c.density;
+        live[(size_t)ot * n_kb + cib * taps + t] = l;
+      }
+    }
+  for (int co = 0; co < c.Cout; ++co)
+    for (int ci = 0; ci < c.Cin; ++ci)
+      for (int t = 0; t < taps; ++t) {
+        const size_t i = ((size_t)co * c.Cin + ci) * taps + t;
+        float v = round16(frand() * wscale * 2.0f, DRNB200_BF16);
+        if (c.identity) v = ((co % c.Cin) == ci) ? 1.0f : 0.0f;
+        const bool l = live[(size_t)(co / c.tile_o) * n_kb + (ci / c.tile_ci) * taps + t];
+        mf[i] = l ? 1.0f : 0.0f;
+        wf[i] = l ? v : 0.0f;
+      }
+  for (int co = 0; co < c.Cout; ++co) {
+    scale[co] = c.identity ? 1.0f : 0.75f + 0.5f * (frand() * 0.5f + 0.5f);
+    shift[co] = c.identity ? 0.0f : 0.1f * frand();
+  }
+
+  float *d_w = dev_upload(wf), *d_m = dev_upload(mf), *d_scale = dev_upload(scale), *d_shift = dev_upload(shift);
+  uint16_t *d_x = dev_upload(x16), *d_res = dev_upload(res16);
+  int32_t *d_rp, *d_kb, *d_nl;
+  CK(cudaMalloc(&d_rp, (n_ot + 1) * 4)); CK(cudaMalloc(&d_kb, (size_t)n_ot * n_kb * 4 + 4)); CK(cudaMalloc(&d_nl, 4));
+  API(drnb200_compact_mask(d_m, c.Cout, c.Cin, c.k, c.k, c.tile_o, c.tile_ci, d_rp, d_kb, d_nl, 0));
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> rp = dev_download(d_rp, n_ot + 1);
+  int32_t nl = dev_download(d_nl, 1)[0];
+  std::vector<int32_t> kb = dev_download(d_kb, (size_t)(nl > 0 ? nl : 1));
+  // check the tile list against the host liveness table
+  int bad_list = 0, wpos = 0;
+  for (int ot = 0; ot < n_ot; ++ot) {
+    if (rp[ot] != wpos) ++bad_list;
+    for (int k2 = 0; k2 < n_kb; ++k2)
+      if (live[(size_t)ot * n_kb + k2]) { if (wpos >= nl || kb[wpos] != k2) ++bad_list; ++wpos; }
+  }
+  if (rp[n_ot] != wpos || nl != wpos) ++bad_list;
+  printf("  tile list: n_live=%d of %d  mismatches=%d\n", nl, n_ot * n_kb, bad_list);
+
+  uint16_t* d_wp;
+  CK(cudaMalloc(&d_wp, (size_t)(nl > 0 ? nl : 1) * c.tile_o * c.tile_ci * 2));
+  API(drnb200_pack_weights(d_w, d_m, c.Cout, c.Cin, c.k, c.k, c.tile_o, c.tile_ci, d_rp, d_kb, c.dt, d_wp, 0));
+  CK(cudaDeviceSynchronize());
+
+  drnb200_conv_desc d{};
+  d.N = c.N; d.H = c.H; d.W = c.W; d.Cin = c.Cin; d.Cout = c.Cout; d.ksize = c.k; d.stride = c.s;
+  d.dilation = c.d; d.relu = c.relu; d.has_residual = c.res; d.act_dtype = c.dt; d.out_f32 = c.out_f32;
+  d.tile_o = c.tile_o; d.tile_ci = c.tile_ci; d.impl = c.impl;
+  drnb200_conv_plan* plan = nullptr;
+  API(drnb200_conv_plan_create(&plan, &d, d_rp, d_kb, d_wp, d_scale, d_shift));
+  printf("  plan impl=%d tile_macs=%lld\n", drnb200_conv_plan_impl(plan),
+         (long long)drnb200_conv_plan_tile_macs(plan));
+  void* d_y;
+  const size_t ybytes = ny * (c.out_f32 ? 4 : 2);
+  CK(cudaMalloc(&d_y, ybytes + 16));
+  CK(cudaMemset(d_y, 0xFF, ybytes));  // NaN pattern: unwritten outputs are caught
+  API(drnb200_conv_forward(plan, d_x, c.res ? d_res : nullptr, d_y, 0));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
+  // timing (3 warm + 5 timed), informative only
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 2; ++i) API(drnb200_conv_forward(plan, d_x, c.res ? d_res : nullptr, d_y, 0));
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < 5; ++i) API(drnb200_conv_forward(plan, d_x, c.res ? d_res : nullptr, d_y, 0));
+  CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+  float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= 5;
+  const double macs = (double)drnb200_conv_plan_tile_macs(plan);
+  printf("  time %.3f ms  -> %.1f TFLOP/s on live tiles\n", ms, 2.0 * macs / (ms * 1e-3) / 1e12);
+
+  std::vector<float> y(ny), ref(ny);
+  if (c.out_f32) y = dev_download((float*)d_y, ny);
+  else {
+    std::vector<uint16_t> y16 = dev_download((uint16_t*)d_y, ny);
+    for (size_t i = 0; i < ny; ++i) y[i] = from16(y16[i], c.dt);
+  }
+  if (c.ref_direct) {
+    drnb200_conv_desc d2 = d; d2.impl = DRNB200_IMPL_DIRECT; d2.out_f32 = 1;
+    drnb200_conv_plan* p2 = nullptr;
+    API(drnb200_conv_plan_create(&p2, &d2, d_rp, d_kb, d_wp, d_scale, d_shift));
+    float* d_y2; CK(cudaMalloc(&d_y2, ny * 4 + 16));
+    API(drnb200_conv_forward(p2, d_x, c.res ? d_res : nullptr, d_y2, 0));
+    CK(cudaDeviceSynchronize());
+    ref = dev_download(d_y2, ny);
+    drnb200_conv_plan_destroy(p2); cudaFree(d_y2);
+  } else {
+    // the packed weights are rounded to c.dt: mirror that on the host
+    std::vector<float> wr(nw);
+    for (size_t i = 0; i < nw; ++i) wr[i] = round16(wf[i], c.dt);
+    cpu_conv(c, xf, wr, scale, shift, resf, ref, OH, OW);
+  }
+  const float tol = c.out_f32 ? 2e-3f : (c.dt == DRNB200_BF16 ? 1.2e-2f : 2e-3f);
+  size_t bad = 0; double maxerr = 0; int shown = 0;
+  for (size_t i = 0; i < ny; ++i) {
+    const float err = fabsf(y[i] - ref[i]);
+    const float lim = tol * fmaxf(1.0f, fabsf(ref[i]));
+    if (!(err <= lim)) {
+      ++bad;
+      if (shown < 12) {
+        const int co = (int)(i % c.Cout); size_t pp = i / c.Cout;
+        const int ox = (int)(pp % OW); pp /= OW; const int oy = (int)(pp % OH); const int n = (int)(pp / OH);
+        printf("    mismatch n=%d oy=%d ox=%d co=%d got=%g want=%g\n", n, oy, ox, co, y[i], ref[i]);
+        ++shown;
+      }
+    }
+    if (err == err && err > maxerr) maxerr = err;
+  }
+  printf("  compare: %zu of %zu outside tol (max abs err %.4g)\n", bad, ny, maxerr);
+  drnb200_conv_plan_destroy(plan);
+  const int ok = (bad == 0 && bad_list == 0);
+  printf("RESULT %s %s\n", c.name, ok ? "PASS" : "FAIL");
+  return ok ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------ stem
+static int run_stem(int dt) {
+  const int N = 2, H = 20, W = 70, C0 = 16;
+  std::vector<float> x((size_t)N * 3 * H * W), w(C0 * 147), sc(C0), sh(C0);
+  for (auto& v : x) v = frand();
+  for (auto& v : w) v = frand() * 0.1f;
+  for (int c = 0; c < C0; ++c) { sc[c] = 1.0f + 0.3f * frand(); sh[c] = 0.2f * frand(); }
+  float *dx = dev_upload(x), *dw = dev_upload(w), *dsc = dev_upload(sc), *dsh = dev_upload(sh);
+  uint16_t* dy; CK(cudaMalloc(&dy, (size_t)N * H * W * C0 * 2));
+  CK(cudaMemset(dy, 0xFF, (size_t)N * H * W * C0 * 2));
+  API(drnb200_stem_forward(dx, dw, dsc, dsh, N, H, W, C0, dt, dy, 0));
+  CK(cudaDeviceSynchronize());
+  std::vector<uint16_t> y = dev_download(dy, (size_t)N * H * W * C0);
+  size_t bad = 0; double maxerr = 0;
+  for (int n = 0; n < N; ++n) for (int oy = 0; oy < H; ++oy) for (int ox = 0; ox < W; ++ox)
+    for (int co = 0; co < C0; ++co) {
+      double acc = 0;
+      for (int ci = 0; ci < 3; ++ci) for (int ky = 0; ky < 7; ++ky) for (int kx = 0; kx < 7; ++kx) {
+        const int iy = oy + ky - 3, ix = ox + kx - 3;
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        acc += (double)x[(((size_t)n * 3 + ci) * H + iy) * W + ix] * w[((co * 3 + ci) * 7 + ky) * 7 + kx];
+      }
+      const float ref = fmaxf((float)acc * sc[co] + sh[co], 0.f);
+      const float got = from16(y[(((size_t)n * H + oy) * W + ox) * C0 + co], dt);
+      const float err = fabsf(got - ref);
+      if (!(err <= 1e-2f * fmaxf(1.f, fabsf(ref)))) { if (bad < 8) printf("    stem mismatch n=%d y=%d x=%d c=%d got=%g want=%g\n", n, oy, ox, co, got, ref); ++bad; }
+      if (err > maxerr) maxerr = err;
+    }
+  printf("  stem: %zu bad, max err %.4g\n", bad, maxerr);
+  printf("RESULT stem_dt%d %s\n", dt, bad ? "FAIL" : "PASS");
+  return bad ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------ head
+static int run_head(int dt, int N, int h, int w) {
+  const int C = 64, classes = 19, H = 8 * h, W = 8 * w;
+  std::vector<uint16_t> x16((size_t)N * h * w * C);
+  std::vector<float> xf(x16.size()), sw((size_t)classes * C), sb(classes);
+  for (size_t i = 0; i < x16.size(); ++i) { x16[i] = to16(frand(), dt); xf[i] = from16(x16[i], dt); }
+  for (auto& v : sw) v = round16(frand() * 0.3f, DRNB200_BF16);
+  for (auto& v : sb) v = 0.1f * frand();
+  uint16_t* dx = dev_upload(x16);
+  float *dsw = dev_upload(sw), *dsb = dev_upload(sb);
+  drnb200_head_plan* plan = nullptr;
+  API(drnb200_head_plan_create(&plan, N, h, w, C, classes, dt, dsw, dsb, 0));
+  uint8_t* dl; float *dseg, *dlp;
+  CK(cudaMalloc(&dl, (size_t)N * H * W)); CK(cudaMalloc(&dseg, (size_t)N * classes * h * w * 4));
+  CK(cudaMalloc(&dlp, (size_t)N * classes * H * W * 4));
+  API(drnb200_head_forward(plan, dx, dl, dseg, dlp, 0));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  head kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
+  std::vector<uint8_t> lab = dev_download(dl, (size_t)N * H * W);
+  std::vector<float> seg = dev_download(dseg, (size_t)N * classes * h * w);
+  std::vector<float> lp = dev_download(dlp, (size_t)N * classes * H * W);
+  // host reference
+  std::vector<float> L((size_t)N * classes * h * w);
+  for (int n = 0; n < N; ++n) for (int c = 0; c < classes; ++c) for (int i = 0; i < h; ++i) for (int j = 0; j < w; ++j) {
+    double acc = sb[c];
+    for (int k = 0; k < C; ++k) acc += (double)xf[(((size_t)n * h + i) * w + j) * C + k] * round16(sw[(size_t)c * C + k], dt);
+    L[(((size_t)n * classes + c) * h + i) * w + j] = (float)acc;
+  }
+  size_t bad_seg = 0, bad_lab = 0, bad_lp = 0, near_tie = 0;
+  for (size_t i = 0; i < L.size(); ++i) if (!(fabsf(L[i] - seg[i]) <= 2e-3f * fmaxf(1.f, fabsf(L[i])))) ++bad_seg;
+  auto wk = [](int k) { return 1.0f - fabsf((float)(2 * k - 15)) / 16.0f; };
+  for (int n = 0; n < N; ++n) for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+    float v[32]; float best = -INFINITY, second = -INFINITY; int arg = 0;
+    for (int c = 0; c < classes; ++c) {
+      double acc = 0;
+      for (int i = 0; i < h; ++i) { const int ky = y + 4 - 8 * i; if (ky < 0 || ky >= 16) continue;
+        for (int j = 0; j < w; ++j) { const int kx = x + 4 - 8 * j; if (kx < 0 || kx >= 16) continue;
+          acc += (double)L[(((size_t)n * classes + c) * h + i) * w + j] * wk(ky) * wk(kx); } }
+      v[c] = (float)acc;
+      if (v[c] > best) { second = best; best = v[c]; arg = c; } else if (v[c] > second) second = v[c];
+    }
+    double s = 0; for (int c = 0; c < classes; ++c) s += exp((double)v[c] - best);
+    const float lse = best + (float)log(s);
+    const uint8_t got = lab[((size_t)n * H + y) * W + x];
+    if (got != arg) { if (best - second < 1e-4f) ++near_tie; else { if (bad_lab < 8) printf("    label mismatch n=%d y=%d x=%d got=%d want=%d\n", n, y, x, got, arg); ++bad_lab; } }
+    for (int c = 0; c < classes; ++c) {
+      const float g = lp[(((size_t)n * classes + c) * H + y) * W + x];
+      if (!(fabsf(g - (v[c] - lse)) <= 2e-3f * fmaxf(1.f, fabsf(v[c] - lse)))) { if (bad_lp < 8) printf("    logprob mismatch n=%d c=%d y=%d x=%d got=%g want=%g\n", n, c, y, x, g, v[c] - lse); ++bad_lp; }
+    }
+  }
+  printf("  head: seg bad=%zu label bad=%zu (near ties %zu) logprob bad=%zu\n", bad_seg, bad_lab, near_tie, bad_lp);
+  drnb200_head_plan_destroy(plan);
+  const int ok = !bad_seg && !bad_lab && !bad_lp;
+  printf("RESULT head_dt%d_%dx%d %s\n", dt, h, w, ok ? "PASS" : "FAIL");
+  return ok ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------ hist
+static int run_hist() {
+  const int64_t n = 1 << 20; const int classes = 19;
+  std::vector<uint8_t> pred(n), lab(n); std::vector<int64_t> lab64(n), ref(classes * classes, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    pred[i] = (uint8_t)((frand() * 0.5f + 0.5f) * classes) % classes;
+    int l = (int)((frand() * 0.5f + 0.5f) * 21); lab[i] = (l >= classes) ? 255 : (uint8_t)l;
+    lab64[i] = (l >= classes) ? 255 : l;
+    if (lab[i] < classes) ref[lab[i] * classes + pred[i]]++;
+  }
+  uint8_t *dp = dev_upload(pred), *dl = dev_upload(lab); int64_t* dl64 = dev_upload(lab64);
+  int64_t* dh; CK(cudaMalloc(&dh, classes * classes * 8)); CK(cudaMemset(dh, 0, classes * classes * 8));
+  API(drnb200_confusion(dp, dl, 0, n, classes, dh, 0));
+  API(drnb200_confusion(dp, dl64, 1, n, classes, dh, 0));
+  CK(cudaDeviceSynchronize());
+  std::vector<int64_t> h = dev_download(dh, (size_t)classes * classes);
+  int bad = 0; for (int i = 0; i < classes * classes; ++i) if (h[i] != 2 * ref[i]) ++bad;
+  int64_t* d64; CK(cudaMalloc(&d64, n * 8)); API(drnb200_labels_to_i64(dp, n, d64, 0)); CK(cudaDeviceSynchronize());
+  std::vector<int64_t> p64 = dev_download(d64, n); for (int64_t i = 0; i < n; ++i) if (p64[i] != pred[i]) { ++bad; break; }
+  printf("RESULT hist %s\n", bad ? "FAIL" : "PASS");
+  return bad ? 1 : 0;
+}
+
+static const ConvCase kCases[] = {
+    // name                N  H   W   Cin Cout k s d relu res dt f32 to  tci impl dens tap ident refdirect
+    {"direct_3x3",         2, 10, 12, 32,  16, 3, 1, 2, 1, 1, 0, 0,  16, 16, 1, 1.0f, 0, 0, 0},
+    {"direct_s2_sparse",   1, 11, 13, 64,  32, 3, 2, 1, 1, 0, 0, 0,  16, 32, 1, 0.5f, 1, 0, 0},
+    {"direct_1x1_f16",     2,  9,  8, 64,  64, 1, 2, 1, 0, 0, 1, 1,  32, 64, 1, 1.0f, 0, 0, 0},
+    {"tcT_ident",          1,  8, 16, 64, 128, 1, 1, 1, 0, 0, 0, 0, 128, 64, 2, 1.0f, 0, 1, 0},
+    {"tcT_1x1",            1,  8, 16, 128,128, 1, 1, 1, 0, 0, 0, 0, 128, 64, 2, 1.0f, 0, 0, 0},
+    {"tcT_3x3_d1",         1,  8, 16, 64, 128, 3, 1, 1, 1, 0, 0, 0, 128, 64, 2, 1.0f, 0, 0, 0},
+    {"tcT_3x3_d2_res",     2, 12, 20, 128,256, 3, 1, 2, 1, 1, 0, 0, 128, 64, 2, 1.0f, 0, 0, 0},
+    {"tcT_3x3_d4_sparse",  2, 16, 32, 256,256, 3, 1, 4, 1, 1, 0, 0, 128, 64, 2, 0.3f, 0, 0, 0},
+    {"tcT_pertap_f16",     1, 16, 32, 128,128, 3, 1, 1, 1, 0, 1, 0, 128, 64, 2, 0.5f, 1, 0, 0},
+    {"tcT_s2",             2, 18, 34, 64, 128, 3, 2, 1, 1, 0, 0, 0, 128, 64, 2, 1.0f, 0, 0, 0},
+    {"tcT_1x1_s2_f32",     1, 16, 32, 64, 128, 1, 2, 1, 0, 0, 0, 1, 128, 64, 2, 1.0f, 0, 0, 0},
+    {"tcT_ci32",           1, 16, 32, 32, 128, 3, 1, 1, 1, 0, 0, 0, 128, 32, 2, 1.0f, 0, 0, 0},
+    {"tcT_big_sparse",     2, 64,128, 512,512, 3, 1, 4, 1, 1, 0, 0, 128, 64, 2, 0.25f,0, 0, 1},
+    {"tcT_big_dense",      2, 64,128, 256,512, 3, 1, 2, 1, 0, 0, 0, 128, 64, 2, 1.0f, 0, 0, 1},
+    {"tcP_16_16",          1, 16, 32, 16,  16, 3, 1, 1, 1, 0, 0, 0,  16, 16, 2, 1.0f, 0, 0, 0},
+    {"tcP_16_32_s2",       2, 18, 34, 16,  32, 3, 2, 1, 1, 0, 0, 0,  32, 16, 2, 1.0f, 0, 0, 0},
+    {"tcP_32_64_s2",       1, 20, 36, 32,  64, 3, 2, 1, 1, 0, 0, 0,  64, 32, 2, 1.0f, 0, 0, 0},
+    {"tcP_64_64_res",      2, 12, 20, 64,  64, 3, 1, 1, 1, 1, 0, 0,  64, 64, 2, 0.6f, 0, 0, 0},
+    {"tcP_1x1_s2",         1, 16, 32, 32,  64, 1, 2, 1, 0, 0, 0, 0,  64, 32, 2, 1.0f, 0, 0, 0},
+    {"tcP_big",            2,128,256, 16,  16, 3, 1, 1, 1, 0, 0, 0,  16, 16, 2, 1.0f, 0, 0, 1},
+};
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    printf("usage: selftest <case>|list\n");
+    return 2;
+  }
+  const std::string name = argv[1];
+  if (name == "list") {
+    for (const auto& c : kCases) printf("%s\n", c.name);
+    printf("stem_bf16\nstem_f16\nhead_bf16\nhead_f16\nhist\n");
+    return 0;
+  }
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) { printf("no CUDA device\n"); return 5; }
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  if (name == "stem_bf16") return run_stem(DRNB200_BF16);
+  if (name == "stem_f16") return run_stem(DRNB200_F16);
+  if (name == "head_bf16") return run_head(DRNB200_BF16, 2, 5, 9);
+  if (name == "head_f16") return run_head(DRNB200_F16, 1, 16, 8);
+  if (name == "hist") return run_hist();
+  for (const auto& c : kCases)
+    if (name == c.name) return run_conv(c);
+  printf("unknown case %s\n", name.c_str());
+  return 2;
+}

@@ -1,0 +1,220 @@
+// common.cuh — error plumbing, 16-bit conversion helpers and the sm_100a PTX wrappers
+// (mbarrier, TMA, tcgen05/TMEM) shared by the kernels of libdrnb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/drnb200.h"
+
+namespace drnb200 {
+
+// ------------------------------------------------------------------ error plumbing (api.cu)
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+
+#define DRN_CUDA(call)                                                   \
+  do {                                                                   \
+    cudaError_t _e = (call);                                             \
+    if (_e != cudaSuccess) return drnb200::cuda_fail(_e, #call);         \
+  } while (0)
+
+#define DRN_REQUIRE(cond, ...)                                           \
+  do {                                                                   \
+    if (!(cond)) { drnb200::set_error(__VA_ARGS__); return DRNB200_E_ARG; } \
+  } while (0)
+
+// ------------------------------------------------------------------ 16-bit storage helpers
+template <int DT> struct Act;  // DT = DRNB200_BF16 / DRNB200_F16
+template <> struct Act<DRNB200_BF16> {
+  __device__ __forceinline__ static float to_f32(uint16_t v) {
+    return __uint_as_float(((uint32_t)v) << 16);
+  }
+  __device__ __forceinline__ static uint16_t from_f32(float f) {
+    return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  }
+};
+template <> struct Act<DRNB200_F16> {
+  __device__ __forceinline__ static float to_f32(uint16_t v) {
+    return __half2float(__ushort_as_half(v));
+  }
+  __device__ __forceinline__ static uint16_t from_f32(float f) {
+    return __half_as_ushort(__float2half_rn(f));
+  }
+};
+
+// Byte offset of 16-byte chunk `chunk` of row `row` inside a K-major tile whose rows are
+// `pitch` bytes (32, 64 or 128) and whose 16-byte chunks are XOR-swizzled the way TMA / UMMA
+// SWIZZLE_{32,64,128}B do (address bits [4,4+B) ^= bits [7,7+B), B = log2(pitch/16)).
+__host__ __device__ __forceinline__ uint32_t swz_offset(uint32_t row, uint32_t chunk, uint32_t pitch) {
+  uint32_t off = row * pitch + chunk * 16u;
+  uint32_t mask = (pitch >> 4) - 1u;         // 1, 3 or 7
+  return off ^ (((off >> 7) & mask) << 4);
+}
+
+// Instruction descriptor for tcgen05.mma kind::f16: D fp32, A/B both bf16 (fmt=1) or fp16 (fmt=0),
+// both K-major, dense, no negate.  bits: [4,6) c_format=1(F32)  [7,10) a_format  [10,13) b_format
+// [15] a_major=0(K)  [16] b_major=0(K)  [17,23) N>>3  [24,29) M>>4
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(int m, int n, int act_dtype) {
+  uint32_t fmt = (act_dtype == DRNB200_BF16) ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ sm_100a PTX wrappers
+
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps (-> "unspecified launch failure") instead of hanging the box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) { __trap(); }
+  }
+}
+
+// ---- TMA
+__device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
+  asm volatile("prefetch.tensormap [%0];\n" ::"l"(desc) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const void* desc, uint64_t* bar, void* smem_dst,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_load(const void* gmem, uint64_t* bar, void* smem_dst,
+                                          uint32_t bytes) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- tcgen05 / TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                   smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 or fp16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::
+                   "r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <- lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor for a K-major tile whose rows are `pitch` bytes
+// (= one swizzle span: 32/64/128 B) stored densely: 8-row groups are 8*pitch bytes apart (SBO).
+//   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   bits [32,46) stride byte offset >> 4   bits [46,48) descriptor version = 1 (Blackwell)
+//   bits [49,52) base offset = 0 (tiles are 1024-byte aligned)      bits [61,64) swizzle: 2=128B, 4=64B, 6=32B
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t pitch) {
+  uint64_t layout = (pitch == 128u) ? 2ull : (pitch == 64u ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                         // LBO (ignored for swizzled K-major layouts)
+  d |= (uint64_t)((8u * pitch) >> 4) << 32;       // SBO
+  d |= (uint64_t)1 << 46;                         // version
+  d |= layout << 61;
+  return d;
+}
+
+
+
+}  // namespace drnb200

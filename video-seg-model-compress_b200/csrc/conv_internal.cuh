@@ -1,0 +1,52 @@
+// conv_internal.cuh — plan object and kernel parameter blocks shared by the conv translation units.
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+#include <vector>
+
+namespace drnb200 {
+
+// parameters common to the direct and tcgen05 kernels (passed by value)
+struct ConvParams {
+  const int32_t* row_ptr;   // [n_ot + 1]
+  const int32_t* kblk;      // [n_live]  kb = cib * taps + tap
+  const uint8_t* w_packed;  // n_live tiles of tile_o x tile_ci 16-bit, swizzled (compact.cu)
+  const float* scale;       // [Cout] folded BatchNorm scale
+  const float* shift;       // [Cout] folded BatchNorm shift
+  const void* x;            // NHWC act_dtype
+  const void* residual;     // NHWC act_dtype or null
+  void* y;                  // NHWC act_dtype (or float32 when out_f32)
+  int N, H, W, OH, OW, Cin, Cout;
+  int taps, stride, dil;
+  int tile_o, tile_ci, n_ot, n_cib;
+  int relu, has_res, out_f32;
+  // ---- tcgen05 path only
+  const int32_t* ot_order;  // output tiles sorted by decreasing live count
+  int TW, TH, tw_shift;     // pixel tile (powers of two), NT = TW*TH
+  int tiles_x, tiles_y, n_pix_tiles, total_tiles;
+  int stages;
+  uint32_t idesc;
+  uint32_t w_tile_bytes, x_tile_bytes, w_stage_bytes, stage_bytes, pitch;
+};
+
+}  // namespace drnb200
+
+struct drnb200_conv_plan {
+  drnb200_conv_desc d;
+  drnb200::ConvParams p;
+  int impl;         // 1 direct, 2 tcgen05
+  int tc_mode;      // 0 = T (M = couts, N = pixels), 1 = P (M = pixels, N = couts)
+  int grid;         // persistent grid size (tcgen05)
+  size_t smem_bytes;
+  int64_t tile_macs;
+  int32_t* d_ot_order;
+  CUtensorMap tmap;        // activations, bound to `tmap_ptr`
+  const void* tmap_ptr;
+  std::vector<int32_t> h_row_ptr;
+};
+
+namespace drnb200 {
+int conv_direct_launch(const drnb200_conv_plan* plan, cudaStream_t st);
+int conv_tc_setup(drnb200_conv_plan* plan);                 // decide tile shapes, smem, attributes
+int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st);
+}  // namespace drnb200

@@ -1,0 +1,436 @@
+// conv_tc.cu — (b) block-sparse implicit-GEMM convolution on tcgen05 / TMEM fed by TMA (sm_100a).
+//
+// GEMM view of one conv layer (reference: tools/get_matrix_shapes.py:19-21, M=Cout, K=Cin*k*k, N=OH*OW):
+//   K is walked as K-blocks kb = (cib, tap): `tile_ci` input channels of one filter tap.  Only the
+//   K-blocks listed as live for the CTA's output-channel tile are loaded and multiplied (compact.cu).
+//   activations: NHWC 16-bit; a K-block of a pixel tile is ONE 4-D TMA box {tile_ci, TW*s, TH*s, 1}
+//                at (cib*tile_ci, ox0*s + (kx-1)*dil, oy0*s + (ky-1)*dil, n); out-of-bounds elements are
+//                zero-filled by TMA, which is exactly the conv's zero padding (padding == dilation);
+//                stride-2 layers use elementStrides = 2.
+//   weights:     pre-packed per live K-block in the swizzled smem image -> one 1-D bulk copy.
+// Two operand orientations share the pipeline:
+//   MODE_T (Cout >= 128): A = weights (M = 128 couts), B = activations (N = NT <= 256 pixels).
+//                         TMEM lane = cout, column = pixel.  The K list is per 128-cout tile, so the
+//                         skipping granularity equals the UMMA M tile and N=256 keeps the MMA at full rate.
+//   MODE_P (Cout <= 64):  A = activations (M = 128 pixels), B = weights (N = Cout).
+//                         TMEM lane = pixel, column = cout (small-channel, bandwidth-bound layers).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = epilogue (TMEM -> registers -> BN affine (+residual) (+ReLU) -> NHWC global).
+// Two accumulator stages in TMEM (2 x 256 columns) let the epilogue of tile i overlap the MMAs of i+1.
+#include "conv_internal.cuh"
+#include <algorithm>
+#include <cudaTypedefs.h>
+
+namespace drnb200 {
+
+constexpr int kTcThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int MODE_T = 0;
+constexpr int MODE_P = 1;
+constexpr uint32_t kTmemCols = 512;
+
+struct __align__(8) TcSync {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct TileCoord {
+  int ot, jb, je, n, ox0, oy0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+  TileCoord c;
+  const int oi = t / p.n_pix_tiles;
+  int pt = t - oi * p.n_pix_tiles;
+  c.ot = __ldg(p.ot_order + oi);
+  c.jb = __ldg(p.row_ptr + c.ot);
+  c.je = __ldg(p.row_ptr + c.ot + 1);
+  const int txi = pt % p.tiles_x;
+  pt /= p.tiles_x;
+  const int tyi = pt % p.tiles_y;
+  c.n = pt / p.tiles_y;
+  c.ox0 = txi * p.TW;
+  c.oy0 = tyi * p.TH;
+  return c;
+}
+
+template <int DT>
+__device__ __forceinline__ float finish(float acc, float sc, float sh, float res, int relu) {
+  float v = fmaf(acc, sc, sh) + res;
+  return relu ? fmaxf(v, 0.f) : v;
+}
+
+template <int MODE, int DT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // tiles must sit on 1024-byte boundaries of the shared window (SWIZZLE_128B atom)
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  TcSync* sync = reinterpret_cast<TcSync*>(smem + (size_t)p.stages * p.stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&sync->full[s], 1);
+      mbar_init(&sync->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&sync->tfull[a], 1);
+      mbar_init(&sync->tempty[a], 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sync->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sync->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const int half = (p.taps == 9) ? 1 : 0;
+      const uint32_t tx_bytes = p.w_tile_bytes + p.x_tile_bytes;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        int kb_next = (c.jb < c.je) ? __ldg(p.kblk + c.jb) : 0;
+        for (int j = c.jb; j < c.je; ++j) {
+          const int kb = kb_next;
+          if (j + 1 < c.je) kb_next = __ldg(p.kblk + j + 1);
+          const int cib = kb / p.taps, tap = kb - cib * p.taps;
+          const int ky = (p.taps == 9) ? tap / 3 : 0, kx = (p.taps == 9) ? tap - ky * 3 : 0;
+          uint8_t* sW = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sX = sW + p.w_stage_bytes;
+          mbar_wait(&sync->empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&sync->full[stage], tx_bytes);
+          bulk_load(p.w_packed + (size_t)j * p.w_tile_bytes, &sync->full[stage], sW, p.w_tile_bytes);
+          tma_load_4d(&tmap, &sync->full[stage], sX, cib * p.tile_ci,
+                      c.ox0 * p.stride + (kx - half) * p.dil, c.oy0 * p.stride + (ky - half) * p.dil,
+                      c.n);
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const int ksteps = (int)(p.pitch / 32u);  // UMMA K = 16 elements = 32 bytes
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        if (c.je == c.jb) continue;  // nothing live: the epilogue does not touch TMEM either
+        mbar_wait(&sync->tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256u;
+        for (int j = c.jb; j < c.je; ++j) {
+          mbar_wait(&sync->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sW = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t sX = sW + p.w_stage_bytes;
+          const uint64_t dW = umma_smem_desc(sW, p.pitch);
+          const uint64_t dX = umma_smem_desc(sX, p.pitch);
+          for (int i = 0; i < ksteps; ++i) {
+            const uint32_t accum = (j > c.jb || i > 0) ? 1u : 0u;
+            if (MODE == MODE_T)
+              umma_f16(d_tmem, dW + (uint64_t)(2 * i), dX + (uint64_t)(2 * i), p.idesc, accum);
+            else
+              umma_f16(d_tmem, dX + (uint64_t)(2 * i), dW + (uint64_t)(2 * i), p.idesc, accum);
+          }
+          umma_commit(&sync->empty[stage]);  // smem slot free once these MMAs retire
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&sync->tfull[acc]);      // accumulator complete
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    uint32_t acc = 0, acc_phase = 0;
+    const uint16_t* res16 = reinterpret_cast<const uint16_t*>(p.residual);
+    uint16_t* y16 = reinterpret_cast<uint16_t*>(p.y);
+    float* y32 = reinterpret_cast<float*>(p.y);
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord c = decode_tile(p, t);
+      const bool live = c.je > c.jb;
+      if (live) {
+        mbar_wait(&sync->tfull[acc], acc_phase);
+        tc_fence_after();
+      }
+      const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
+
+      if (MODE == MODE_T) {
+        // lane = output channel, columns = pixels of the tile
+        const int co = c.ot * 128 + q * 32 + lane;
+        const float sc = __ldg(p.scale + co), sh = __ldg(p.shift + co);
+        const int nt = p.TW * p.TH;
+        for (int ch = 0; ch < nt; ch += 32) {
+          uint32_t v[32];
+          if (live) {
+            tmem_ld32(t_addr + (uint32_t)ch, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = ch + i;
+            const int oy = c.oy0 + (j >> p.tw_shift), ox = c.ox0 + (j & (p.TW - 1));
+            if (oy < p.OH && ox < p.OW) {
+              const size_t off = (((size_t)c.n * p.OH + oy) * p.OW + ox) * p.Cout + co;
+              const float r = p.has_res ? Act<DT>::to_f32(__ldg(res16 + off)) : 0.f;
+              const float o = finish<DT>(__uint_as_float(v[i]), sc, sh, r, p.relu);
+              if (p.out_f32) y32[off] = o;
+              else y16[off] = Act<DT>::from_f32(o);
+            }
+          }
+        }
+      } else {
+        // lane = pixel of the tile (M = 128), columns = output channels (N = Cout)
+        const int j = q * 32 + lane;
+        const int oy = c.oy0 + (j >> p.tw_shift), ox = c.ox0 + (j & (p.TW - 1));
+        const bool valid = (oy < p.OH) && (ox < p.OW);
+        const size_t off0 = (((size_t)c.n * p.OH + oy) * p.OW + ox) * p.Cout;
+        for (int cb = 0; cb < p.Cout; cb += 16) {
+          uint32_t v[16];
+          if (live) {
+            tmem_ld16(t_addr + (uint32_t)cb, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
+          }
+          if (valid) {
+            float r[16];
+            if (p.has_res) {
+              const uint4* rp = reinterpret_cast<const uint4*>(res16 + off0 + cb);
+              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                r[2 * i] = Act<DT>::to_f32((uint16_t)(rw[i] & 0xFFFFu));
+                r[2 * i + 1] = Act<DT>::to_f32((uint16_t)(rw[i] >> 16));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = 0.f;
+            }
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              o[i] = finish<DT>(__uint_as_float(v[i]), __ldg(p.scale + cb + i),
+                                __ldg(p.shift + cb + i), r[i], p.relu);
+            if (p.out_f32) {
+              float4* yp = reinterpret_cast<float4*>(y32 + off0 + cb);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                yp[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            } else {
+              uint32_t w[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                w[i] = (uint32_t)Act<DT>::from_f32(o[2 * i]) |
+                       ((uint32_t)Act<DT>::from_f32(o[2 * i + 1]) << 16);
+              uint4* yp = reinterpret_cast<uint4*>(y16 + off0 + cb);
+              yp[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              yp[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+          }
+        }
+      }
+
+      if (live) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sync->tempty[acc]);
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+  return fn;
+}
+
+static int pow2_ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+static int ilog2(int v) {
+  int r = 0;
+  while ((1 << r) < v) ++r;
+  return r;
+}
+
+template <int MODE, int DT>
+static int set_attr(size_t smem) {
+  DRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, DT>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return DRNB200_OK;
+}
+
+int conv_tc_setup(drnb200_conv_plan* plan) {
+  ConvParams& p = plan->p;
+  const drnb200_conv_desc& d = plan->d;
+  // ---- shape support
+  const bool ci_ok = (p.tile_ci == 16 || p.tile_ci == 32 || p.tile_ci == 64);
+  const bool k_ok = (d.ksize == 1 || d.ksize == 3) && (d.stride == 1 || d.stride == 2);
+  int mode = -1;
+  if (ci_ok && k_ok) {
+    if (p.tile_o == 128 && p.Cout % 128 == 0) mode = MODE_T;
+    else if (p.tile_o == p.Cout && p.Cout % 16 == 0 && p.Cout <= 256) mode = MODE_P;
+  }
+  if (mode < 0) {
+    set_error("tcgen05 conv: unsupported shape Cin=%d Cout=%d k=%d s=%d tile=%dx%d", d.Cin, d.Cout,
+              d.ksize, d.stride, p.tile_o, p.tile_ci);
+    return DRNB200_E_ARG;
+  }
+  plan->tc_mode = mode;
+  // ---- pixel tile
+  const int nt_max = (mode == MODE_T) ? 256 : 128;
+  int TW = std::min(std::min(pow2_ceil(p.OW), nt_max), 256 / d.stride);
+  int TH = std::min(pow2_ceil(p.OH), nt_max / TW);
+  if (mode == MODE_P) TH = 128 / TW;           // UMMA M is exactly 128 pixels
+  while (TW * TH < 32) TH <<= 1;               // epilogue walks 32-column chunks
+  if (TH * d.stride > 256) {
+    set_error("tcgen05 conv: pixel tile %dx%d does not fit a TMA box", TW, TH);
+    return DRNB200_E_ARG;
+  }
+  p.TW = TW; p.TH = TH; p.tw_shift = ilog2(TW);
+  p.tiles_x = (p.OW + TW - 1) / TW;
+  p.tiles_y = (p.OH + TH - 1) / TH;
+  p.n_pix_tiles = p.N * p.tiles_x * p.tiles_y;
+  p.total_tiles = p.n_pix_tiles * p.n_ot;
+  const int NT = TW * TH;
+  p.pitch = (uint32_t)p.tile_ci * 2u;
+  p.w_tile_bytes = (uint32_t)p.tile_o * p.pitch;
+  p.x_tile_bytes = (uint32_t)NT * p.pitch;
+  p.w_stage_bytes = (p.w_tile_bytes + 1023u) & ~1023u;
+  p.stage_bytes = p.w_stage_bytes + ((p.x_tile_bytes + 1023u) & ~1023u);
+  p.idesc = (mode == MODE_T) ? umma_idesc_f16(128, NT, d.act_dtype)
+                             : umma_idesc_f16(128, p.Cout, d.act_dtype);
+  // ---- shared memory: as many stages as fit in 227 KB (also pins one CTA per SM: TMEM is taken whole)
+  const size_t kMaxSmem = 232448;
+  const size_t fixed = 1024 + sizeof(TcSync);
+  int stages = (int)((kMaxSmem - fixed) / p.stage_bytes);
+  stages = std::max(2, std::min(stages, kMaxStages));
+  p.stages = stages;
+  plan->smem_bytes = kMaxSmem;
+  int rc;
+  if (mode == MODE_T)
+    rc = (d.act_dtype == DRNB200_BF16) ? set_attr<MODE_T, DRNB200_BF16>(plan->smem_bytes)
+                                       : set_attr<MODE_T, DRNB200_F16>(plan->smem_bytes);
+  else
+    rc = (d.act_dtype == DRNB200_BF16) ? set_attr<MODE_P, DRNB200_BF16>(plan->smem_bytes)
+                                       : set_attr<MODE_P, DRNB200_F16>(plan->smem_bytes);
+  if (rc) return rc;
+  // ---- work list: output tiles by decreasing live count, so the round-robin persistent schedule
+  //      gives every CTA tiles of equal length at the same step (block-sparse load balance)
+  std::vector<int32_t> order(p.n_ot);
+  for (int i = 0; i < p.n_ot; ++i) order[i] = i;
+  const std::vector<int32_t>& rp = plan->h_row_ptr;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return (rp[a + 1] - rp[a]) > (rp[b + 1] - rp[b]);
+  });
+  DRN_CUDA(cudaMalloc((void**)&plan->d_ot_order, sizeof(int32_t) * p.n_ot));
+  DRN_CUDA(cudaMemcpy(plan->d_ot_order, order.data(), sizeof(int32_t) * p.n_ot,
+                      cudaMemcpyHostToDevice));
+  p.ot_order = plan->d_ot_order;
+  int dev = 0, sms = 148;
+  DRN_CUDA(cudaGetDevice(&dev));
+  DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  plan->grid = std::min(p.total_tiles, sms);
+  plan->tmap_ptr = nullptr;
+  return DRNB200_OK;
+}
+
+static int encode_tmap(drnb200_conv_plan* plan, const void* x) {
+  const ConvParams& p = plan->p;
+  const drnb200_conv_desc& d = plan->d;
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return DRNB200_E_CUDA;
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+  cuuint64_t gstr[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.W * p.Cin * 2,
+                        (cuuint64_t)p.H * p.W * p.Cin * 2};
+  cuuint32_t box[4] = {(cuuint32_t)p.tile_ci, (cuuint32_t)(p.TW * d.stride),
+                       (cuuint32_t)(p.TH * d.stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+  CUtensorMapSwizzle sw = p.pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : p.pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                          : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMapDataType dt = d.act_dtype == DRNB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(&plan->tmap, dt, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (Cin=%d W=%d H=%d N=%d box=%u,%u,%u)",
+              (int)r, p.Cin, p.W, p.H, p.N, box[0], box[1], box[2]);
+    return DRNB200_E_CUDA;
+  }
+  plan->tmap_ptr = x;
+  return DRNB200_OK;
+}
+
+int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st) {
+  const ConvParams& p = plan->p;
+  if (plan->tmap_ptr != p.x) {
+    int rc = encode_tmap(plan, p.x);
+    if (rc) return rc;
+  }
+  if (p.total_tiles == 0) return DRNB200_OK;
+  const dim3 grid(plan->grid), block(kTcThreads);
+  const bool bf = plan->d.act_dtype == DRNB200_BF16;
+  if (plan->tc_mode == MODE_T) {
+    if (bf) conv_tc_kernel<MODE_T, DRNB200_BF16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, p);
+    else    conv_tc_kernel<MODE_T, DRNB200_F16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, p);
+  } else {
+    if (bf) conv_tc_kernel<MODE_P, DRNB200_BF16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, p);
+    else    conv_tc_kernel<MODE_P, DRNB200_F16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, p);
+  }
+  DRN_CUDA(cudaGetLastError());
+  return DRNB200_OK;
+}
+
+}  // namespace drnb200
