@@ -1,0 +1,397 @@
+"""CUDA engine behind :class:`drnb200.DRNSeg` — turns the module tree into a list of kernel launches.
+
+Per conv layer the engine keeps a *derived cache* of (tile list, packed 16-bit weights, folded BN affine,
+C-ABI plan): the fp32 OIHW ``nn.Parameter`` stays the source of truth because the reference's pruners
+read and mutate ``model.state_dict()[key]`` in place (pruners/Pruner.py:17-20).  The cache is keyed on
+the tensors' ``_version`` counters and rebuilt when stale.
+
+Data layout in HBM: activations NHWC 16-bit (bf16 or fp16, ``act_dtype``), one buffer per layer output
+drawn from a size-keyed pool; packed weights = live K-blocks only, in the swizzled shared-memory image.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import ffi
+from .drn import BasicBlock, Bottleneck
+
+_DT = {"bf16": ffi.BF16, "fp16": ffi.F16, "f16": ffi.F16}
+
+
+def _pick_tiles(cin, cout):
+    """tile-list granularity the kernels consume: K-blocks of 64/32/16 input channels; 128-cout output
+    tiles on the wide layers (MODE_T), the whole cout range on the narrow ones (MODE_P)."""
+    tile_ci = 64 if cin % 64 == 0 else 32 if cin % 32 == 0 else 16 if cin % 16 == 0 else None
+    if tile_ci is None:
+        raise ffi.Drnb200Error("Cin=%d is not a multiple of 16" % cin)
+    if cout % 128 == 0:
+        tile_o = 128
+    elif cout % 16 == 0 and cout <= 256:
+        tile_o = cout
+    elif cout % 8 == 0:
+        tile_o = 8
+    else:
+        raise ffi.Drnb200Error("Cout=%d is not a multiple of 8" % cout)
+    return tile_o, tile_ci
+
+
+class ConvLayer:
+    """one conv (+BN) (+residual) (+ReLU) of the network and its derived device-side cache"""
+
+    def __init__(self, key, conv, bn, relu, residual_from=None, input_from=None):
+        self.key = key                  # state_dict key prefix of the conv, e.g. 'layer.3.0.conv1'
+        self.conv, self.bn, self.relu = conv, bn, relu
+        self.input_from = input_from    # index of the op whose output feeds this conv (None = previous)
+        self.residual_from = residual_from
+        self.out_f32 = False
+        self.version = None
+        self.row_ptr = self.kblk = self.w_packed = self.scale = self.shift = None
+        self.n_live = 0
+        self.tile_o = self.tile_ci = None
+        self.live_elems = 0             # surviving weight elements (Pruner.print_stats numerator)
+        self.plans = {}
+
+    # ---- mask ingestion -----------------------------------------------------------------------
+    def weight_and_mask(self, mask_dict):
+        conv = self.conv
+        if hasattr(conv, "weight_orig") and hasattr(conv, "weight_mask"):   # torch.nn.utils.prune
+            return conv.weight_orig.detach(), conv.weight_mask.detach(), (
+                conv.weight_orig._version, conv.weight_mask._version)
+        w = conv.weight.detach()
+        if mask_dict is not None:
+            for k in (self.key + ".weight", "module." + self.key + ".weight"):
+                if k in mask_dict:
+                    m = mask_dict[k]
+                    return w, m, (w._version, id(m), m._version)
+        return w, None, (w._version,)
+
+    def destroy_plans(self):
+        lib = ffi.lib()
+        for p in self.plans.values():
+            lib.drnb200_conv_plan_destroy(p)
+        self.plans = {}
+
+    def refresh(self, mask_dict, act_dtype, device):
+        """(re)build tile list, packed weights and BN affine if the parameters changed"""
+        w, m, ver = self.weight_and_mask(mask_dict)
+        bn = self.bn
+        ver = ver + (act_dtype, bn.weight._version, bn.bias._version, bn.running_mean._version,
+                     bn.running_var._version) if bn is not None else ver + (act_dtype,)
+        if ver == self.version:
+            return False
+        lib = ffi.lib()
+        self.destroy_plans()
+        O, I, kh, kw = w.shape
+        self.tile_o, self.tile_ci = _pick_tiles(I, O)
+        w32 = w.to(device=device, dtype=torch.float32).contiguous()
+        if m is None:
+            mask32 = (w32 != 0).to(torch.float32)          # liveness from zeros (semantic_seg.py test path)
+        else:
+            mask32 = (m.to(device=device) != 0).to(torch.float32).contiguous()   # Hb masks may exceed 1
+        n_ot, n_kb = O // self.tile_o, (I // self.tile_ci) * kh * kw
+        self.row_ptr = torch.empty(n_ot + 1, dtype=torch.int32, device=device)
+        self.kblk = torch.empty(max(1, n_ot * n_kb), dtype=torch.int32, device=device)
+        n_live = torch.zeros(1, dtype=torch.int32, device=device)
+        st = ffi.stream_ptr()
+        ffi.check(lib.drnb200_compact_mask(ffi.ptr(mask32), O, I, kh, kw, self.tile_o, self.tile_ci,
+                                           ffi.ptr(self.row_ptr), ffi.ptr(self.kblk), ffi.ptr(n_live), st),
+                  "compact_mask(%s)" % self.key)
+        self.n_live = int(n_live.item())
+        self.w_packed = torch.empty(max(1, self.n_live) * self.tile_o * self.tile_ci, dtype=torch.int16,
+                                    device=device)
+        ffi.check(lib.drnb200_pack_weights(ffi.ptr(w32), ffi.ptr(mask32), O, I, kh, kw, self.tile_o,
+                                           self.tile_ci, ffi.ptr(self.row_ptr), ffi.ptr(self.kblk),
+                                           act_dtype, ffi.ptr(self.w_packed), st),
+                  "pack_weights(%s)" % self.key)
+        self.live_elems = int(torch.count_nonzero(w32 * mask32).item())
+        if bn is not None:      # BatchNorm2d eval: y = (x-mean)/sqrt(var+eps)*gamma+beta  (drn.py:7)
+            inv = torch.rsqrt(bn.running_var.detach().to(device, torch.float32) + bn.eps)
+            self.scale = (bn.weight.detach().to(device, torch.float32) * inv).contiguous()
+            self.shift = (bn.bias.detach().to(device, torch.float32)
+                          - bn.running_mean.detach().to(device, torch.float32) * self.scale).contiguous()
+        else:
+            self.scale = torch.ones(O, dtype=torch.float32, device=device)
+            self.shift = torch.zeros(O, dtype=torch.float32, device=device)
+        self.version = ver
+        return True
+
+    def plan(self, N, H, W, act_dtype, impl):
+        k = (N, H, W, act_dtype, impl, self.out_f32)
+        p = self.plans.get(k)
+        if p is None:
+            conv = self.conv
+            d = ffi.ConvDesc(N=N, H=H, W=W, Cin=conv.in_channels, Cout=conv.out_channels,
+                             ksize=conv.kernel_size[0], stride=conv.stride[0], dilation=conv.dilation[0],
+                             relu=int(self.relu), has_residual=int(self.residual_from is not None),
+                             act_dtype=act_dtype, out_f32=int(self.out_f32), tile_o=self.tile_o,
+                             tile_ci=self.tile_ci, impl=impl)
+            h = C.c_void_p()
+            ffi.check(ffi.lib().drnb200_conv_plan_create(
+                C.byref(h), C.byref(d), ffi.ptr(self.row_ptr), ffi.ptr(self.kblk), ffi.ptr(self.w_packed),
+                ffi.ptr(self.scale), ffi.ptr(self.shift)), "conv_plan_create(%s)" % self.key)
+            p = self.plans[k] = h
+        return p
+
+    def out_hw(self, H, W):
+        s = self.conv.stride[0]
+        return (H - 1) // s + 1, (W - 1) // s + 1
+
+
+def _check_conv(conv, key):
+    k, s, d, p = conv.kernel_size, conv.stride, conv.dilation, conv.padding
+    ok = (k[0] == k[1] and k[0] in (1, 3) and s[0] == s[1] and d[0] == d[1] and conv.groups == 1
+          and conv.bias is None and p[0] == p[1] == d[0] * (k[0] // 2))
+    if not ok:
+        raise ffi.Drnb200Error("conv %s: unsupported configuration %r" % (key, conv))
+
+
+class Engine:
+    """builds and runs the launch list for one DRNSeg module"""
+
+    def __init__(self, seg_module, act_dtype="bf16", conv_impl=ffi.IMPL_AUTO):
+        self.m = seg_module
+        self.act_dtype = _DT[act_dtype] if isinstance(act_dtype, str) else int(act_dtype)
+        self.conv_impl = conv_impl
+        self.mask_dict = None
+        self.stem = None       # (conv, bn)
+        self.ops = []          # ConvLayer list in execution order
+        self.head_plans = {}
+        self.head_version = None
+        self.launches_per_forward = 0
+        self._build_graph()
+
+    # ---- module tree -> op list ----------------------------------------------------------------
+    def _build_graph(self):
+        root = getattr(self.m, "layer", None)
+        prefix = "layer"
+        if root is None:
+            root, prefix = self.m.base, "base"        # seg_video.py:79 flavour
+        ops = []
+        pending = {"conv": None, "key": None}
+
+        def flush_plain(bn, relu):
+            conv, key = pending["conv"], pending["key"]
+            pending["conv"] = None
+            if conv.kernel_size[0] == 7:
+                if conv.in_channels != 3 or conv.out_channels != 16 or self.stem is not None or ops:
+                    raise ffi.Drnb200Error("unexpected 7x7 conv %s" % key)
+                self.stem = (conv, bn, key)
+                if not relu:
+                    raise ffi.Drnb200Error("stem without ReLU is not supported")
+                return
+            _check_conv(conv, key)
+            ops.append(ConvLayer(key, conv, bn, relu))
+
+        def walk(mod, key):
+            children = list(mod.named_children())
+            if isinstance(mod, BasicBlock):
+                src = len(ops) - 1          # output index feeding this block (-1 = stem output)
+                _check_conv(mod.conv1, key + ".conv1"); _check_conv(mod.conv2, key + ".conv2")
+                ops.append(ConvLayer(key + ".conv1", mod.conv1, mod.bn1, True, input_from=src))
+                res = None
+                if getattr(mod, "residual", True):
+                    res = src
+                    if mod.downsample is not None:
+                        dconv, dbn = mod.downsample[0], mod.downsample[1]
+                        _check_conv(dconv, key + ".downsample.0")
+                        ops.append(ConvLayer(key + ".downsample.0", dconv, dbn, False, input_from=src))
+                        res = len(ops) - 1
+                c1 = len(ops) - 1 if res is None or mod.downsample is None else len(ops) - 2
+                ops.append(ConvLayer(key + ".conv2", mod.conv2, mod.bn2, True, residual_from=res,
+                                     input_from=c1))
+                return
+            if isinstance(mod, Bottleneck):
+                src = len(ops) - 1
+                for n in ("conv1", "conv2", "conv3"):
+                    _check_conv(getattr(mod, n), key + "." + n)
+                ops.append(ConvLayer(key + ".conv1", mod.conv1, mod.bn1, True, input_from=src))
+                ops.append(ConvLayer(key + ".conv2", mod.conv2, mod.bn2, True))
+                c2 = len(ops) - 1
+                res = src
+                if mod.downsample is not None:
+                    dconv, dbn = mod.downsample[0], mod.downsample[1]
+                    _check_conv(dconv, key + ".downsample.0")
+                    ops.append(ConvLayer(key + ".downsample.0", dconv, dbn, False, input_from=src))
+                    res = len(ops) - 1
+                ops.append(ConvLayer(key + ".conv3", mod.conv3, mod.bn3, True, residual_from=res,
+                                     input_from=c2))
+                return
+            if isinstance(mod, nn.Conv2d):
+                if pending["conv"] is not None:
+                    raise ffi.Drnb200Error("conv %s is not followed by BatchNorm" % pending["key"])
+                pending["conv"], pending["key"] = mod, key
+                return
+            if isinstance(mod, nn.BatchNorm2d):
+                if pending["conv"] is None:
+                    raise ffi.Drnb200Error("BatchNorm %s without a conv" % key)
+                pending["bn"] = mod
+                return
+            if isinstance(mod, nn.ReLU):
+                if pending["conv"] is not None:
+                    flush_plain(pending.pop("bn"), True)
+                return
+            if isinstance(mod, nn.Sequential) or children:
+                for name, child in children:
+                    walk(child, key + "." + name)
+                    # a conv+bn pair not followed by ReLU inside this container
+                return
+            raise ffi.Drnb200Error("unsupported module %s: %r" % (key, mod))
+
+        walk(root, prefix)
+        if pending["conv"] is not None:
+            raise ffi.Drnb200Error("dangling conv %s" % pending["key"])
+        if self.stem is None or not ops:
+            raise ffi.Drnb200Error("could not find the DRN stem / conv stages")
+        self.ops = ops
+
+    # ---- parameters -> device caches -----------------------------------------------------------
+    def set_masks(self, mask_dict):
+        """attach a Pruner.mask_dict (pruners/Pruner.py:13); None = derive liveness from zeros"""
+        self.mask_dict = mask_dict
+
+    def refresh(self, device):
+        rebuilt = 0
+        for op in self.ops:
+            rebuilt += bool(op.refresh(self.mask_dict, self.act_dtype, device))
+        conv, bn, _ = self.stem
+        ver = (conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version,
+               bn.running_var._version, str(device))
+        if getattr(self, "_stem_version", None) != ver:
+            inv = torch.rsqrt(bn.running_var.detach().to(device, torch.float32) + bn.eps)
+            self.stem_scale = (bn.weight.detach().to(device, torch.float32) * inv).contiguous()
+            self.stem_shift = (bn.bias.detach().to(device, torch.float32)
+                               - bn.running_mean.detach().to(device, torch.float32) * self.stem_scale
+                               ).contiguous()
+            self.stem_w = conv.weight.detach().to(device, torch.float32).contiguous()
+            self._stem_version = ver
+        seg = self.m.seg
+        hver = (seg.weight._version, seg.bias._version, self.act_dtype, str(device))
+        if self.head_version != hver:
+            lib = ffi.lib()
+            for p in self.head_plans.values():
+                lib.drnb200_head_plan_destroy(p)
+            self.head_plans = {}
+            self.seg_w = seg.weight.detach().to(device, torch.float32).reshape(seg.out_channels, -1).contiguous()
+            self.seg_b = seg.bias.detach().to(device, torch.float32).contiguous()
+            self.head_version = hver
+        return rebuilt
+
+    def _head_plan(self, N, h, w):
+        k = (N, h, w)
+        p = self.head_plans.get(k)
+        if p is None:
+            hdl = C.c_void_p()
+            seg = self.m.seg
+            ffi.check(ffi.lib().drnb200_head_plan_create(
+                C.byref(hdl), N, h, w, seg.in_channels, seg.out_channels, self.act_dtype,
+                ffi.ptr(self.seg_w), ffi.ptr(self.seg_b), ffi.stream_ptr()), "head_plan_create")
+            p = self.head_plans[k] = hdl
+        return p
+
+    # ---- statistics ----------------------------------------------------------------------------
+    def mac_counts(self, N, H, W):
+        """(dense MACs, unpruned-element MACs, live-tile MACs) of the conv stack incl. stem and seg,
+        per forward of an [N,3,H,W] batch — numerators for tensor-pipe utilisation."""
+        dense = live = tile = 0
+        h, w = H, W
+        sconv = self.stem[0]
+        stem_macs = N * H * W * sconv.out_channels * 147
+        dense += stem_macs; live += stem_macs; tile += stem_macs
+        shapes = {-1: (H, W)}
+        for i, op in enumerate(self.ops):
+            src = op.input_from if op.input_from is not None else i - 1
+            ih, iw = shapes[src]
+            oh, ow = op.out_hw(ih, iw)
+            shapes[i] = (oh, ow)
+            px = N * oh * ow
+            c = op.conv
+            dense += px * c.out_channels * c.in_channels * c.kernel_size[0] ** 2
+            live += px * op.live_elems
+            tile += px * op.n_live * op.tile_o * op.tile_ci
+        oh, ow = shapes[len(self.ops) - 1]
+        seg = N * oh * ow * self.m.seg.in_channels * self.m.seg.out_channels
+        return dense + seg, live + seg, tile + seg
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def run(self, x, want_labels=True, want_logprob=False, want_seg=False):
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3):
+            raise ffi.Drnb200Error("input must be a float32 CUDA tensor [N,3,H,W] (got %s %s on %s); "
+                                   "there is no CPU path" % (tuple(x.shape), x.dtype, x.device))
+        N, _, H, W = x.shape
+        if H % 8 or W % 8:
+            raise ffi.Drnb200Error("H and W must be multiples of 8 (got %dx%d)" % (H, W))
+        x = x.contiguous()
+        dev = x.device
+        lib = ffi.lib()
+        self.refresh(dev)
+        st = ffi.stream_ptr()
+        adt = self.act_dtype
+        launches = 0
+        # last conv hands float32? (kept 16-bit in round 1: the head GEMM consumes act_dtype)
+        outs = {}
+        shapes = {-1: (H, W)}
+        # liveness of buffers for pooling
+        last_use = {}
+        for i, op in enumerate(self.ops):
+            src = op.input_from if op.input_from is not None else i - 1
+            last_use[src] = i
+            if op.residual_from is not None:
+                last_use[op.residual_from] = i
+        last_use[len(self.ops) - 1] = len(self.ops)      # consumed by the head
+        pool = {}
+
+        def take(nelem):
+            lst = pool.get(nelem)
+            if lst:
+                return lst.pop()
+            return torch.empty(nelem, dtype=torch.int16, device=dev)
+
+        def give(idx):
+            t = outs.pop(idx, None)
+            if t is not None:
+                pool.setdefault(t.numel(), []).append(t)
+
+        sconv = self.stem[0]
+        c0 = sconv.out_channels
+        y = take(N * H * W * c0)
+        ffi.check(lib.drnb200_stem_forward(ffi.ptr(x), ffi.ptr(self.stem_w), ffi.ptr(self.stem_scale),
+                                           ffi.ptr(self.stem_shift), N, H, W, c0, adt, ffi.ptr(y), st),
+                  "stem_forward")
+        launches += 1
+        outs[-1] = y
+        for i, op in enumerate(self.ops):
+            src = op.input_from if op.input_from is not None else i - 1
+            ih, iw = shapes[src]
+            oh, ow = op.out_hw(ih, iw)
+            shapes[i] = (oh, ow)
+            plan = op.plan(N, ih, iw, adt, self.conv_impl)
+            yo = take(N * oh * ow * op.conv.out_channels)
+            res = outs[op.residual_from] if op.residual_from is not None else None
+            ffi.check(lib.drnb200_conv_forward(plan, ffi.ptr(outs[src]), ffi.ptr(res), ffi.ptr(yo), st),
+                      "conv_forward(%s)" % op.key)
+            launches += 1
+            outs[i] = yo
+            for j in [k for k, last in last_use.items() if last == i]:
+                give(j)
+        last = len(self.ops) - 1
+        h8, w8 = shapes[last]
+        hp = self._head_plan(N, h8, w8)
+        classes = self.m.seg.out_channels
+        labels = torch.empty((N, 8 * h8, 8 * w8), dtype=torch.uint8, device=dev) if want_labels else None
+        logprob = torch.empty((N, classes, 8 * h8, 8 * w8), dtype=torch.float32, device=dev) \
+            if want_logprob else None
+        seg = torch.empty((N, classes, h8, w8), dtype=torch.float32, device=dev) if want_seg else None
+        ffi.check(lib.drnb200_head_forward(hp, ffi.ptr(outs[last]), ffi.ptr(labels), ffi.ptr(seg),
+                                           ffi.ptr(logprob), st), "head_forward")
+        launches += 1 + int(want_labels or want_logprob) + int(want_seg)
+        self.launches_per_forward = launches
+        return labels, logprob, seg
+
+    def close(self):
+        lib = ffi.lib()
+        for op in self.ops:
+            op.destroy_plans()
+        for p in self.head_plans.values():
+            lib.drnb200_head_plan_destroy(p)
+        self.head_plans = {}
