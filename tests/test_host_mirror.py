@@ -1,0 +1,233 @@
+"""Host-side mirror (video-seg-model-compress_b200/drnb200) against fixtures generated from the real reference.
+CPU only: module tree / state_dict keys, every pruner's masks, BSR text export, C-ABI symbol table."""
+import collections
+import ctypes
+import io
+import json
+import os
+import re
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+
+import drnb200
+from drnb200 import ffi
+from drnb200.pruners import (BlockPruner, BlockPrunerConfig, BlockletType, GroupingPruner,
+                             GroupingPrunerConfig, HbPruner, HbPrunerConfig, RmbPruner, RmbPrunerConfig,
+                             RmcdbPruner, RmcdbPrunerConfig, SRMBRepMasker, SRMBRepMaskerConfig, make_pruner)
+from conftest import ROOT
+from helpers import golden, load_keys
+from oracle import recipe
+
+MASKS = np.load(golden("pruner_masks.npz"))
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def _w(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)).numpy()
+
+
+W_A, W_B, W_C = _w((64, 32, 3, 3), 11), _w((32, 64, 1, 1), 12), _w((24, 20, 3, 3), 13)
+
+
+def _same(name, mask):
+    ref = recipe.unpack_mask_bits(MASKS[name], mask.shape)
+    got = (np.asarray(mask) != 0).astype(np.float32)
+    assert np.array_equal(got, ref), name
+
+
+@pytest.mark.parametrize("arch", ["drn_d_22", "drn_d_38", "drn_d_54", "drn_c_26"])
+def test_state_dict_keys_and_shapes(arch):
+    ref = load_keys(arch)
+    m = drnb200.DRNSeg(arch, 19, pretrained_model=None, pretrained=False)
+    mine = collections.OrderedDict((k, tuple(v.shape)) for k, v in m.state_dict().items())
+    assert list(mine.items()) == list(ref.items())
+    base = drnb200.DRNSeg(arch, 19, pretrained=False, backbone_attr="base")
+    assert [k.replace("base.", "layer.", 1) for k in base.state_dict()] == list(ref.keys())
+
+
+def test_up_weight_is_the_reference_kernel():
+    m = drnb200.DRNSeg("drn_d_22", 19, pretrained=False)
+    assert np.array_equal(m.up.weight[0, 0].numpy(), np.load(golden("up_weight_row.npy")))
+    assert m.up.weight.requires_grad is False and tuple(m.up.weight.shape) == (19, 1, 16, 16)
+    assert len(list(m.optim_parameters())) == len(list(m.layer.parameters())) + 2
+
+
+def test_engine_graph_matches_module_tree():
+    for arch, n_convs in (("drn_d_22", 24), ("drn_d_38", 40), ("drn_d_54", 56), ("drn_c_26", 29)):
+        m = drnb200.DRNSeg(arch, 19, pretrained=False)
+        eng = m.engine()
+        convs = [k for k, s in load_keys(arch).items() if len(s) == 4 and s[2] in (1, 3) and k.startswith("layer.")]
+        assert sorted(op.key + ".weight" for op in eng.ops) == sorted(convs)
+        assert len(eng.ops) == n_convs
+        for i, op in enumerate(eng.ops):
+            assert op.input_from is None or op.input_from < i
+            assert op.residual_from is None or op.residual_from < i
+
+
+def test_cuda_path_fails_loudly_without_gpu_input():
+    m = drnb200.DRNSeg("drn_d_22", 19, pretrained=False)
+    with pytest.raises(ffi.Drnb200Error):
+        m(torch.zeros(1, 3, 64, 64))          # CPU tensor: there is no CPU fallback
+    with pytest.raises(RuntimeError):
+        drnb200.DRNSeg("drn_d_22", 19)        # pretrained=True needs the model zoo
+
+
+BLOCK_CASES = {
+    "block_a_uncollapsed": (W_A, (0.75, 16, 8, -1, -1, False)),
+    "block_a_collapsed": (W_A, (0.5, 8, 24, -1, -1, True)),
+    "block_a_sub": (W_A, (0.5, 8, 4, 32, 16, False)),
+    "block_b_1x1conv": (W_B, (0.75, 8, 16, -1, -1, False)),
+    "block_c_ragged": (W_C, (0.6, 16, 8, -1, -1, False)),
+    "block_a_unstructured": (W_A, (0.9, 1, 1, -1, -1, True)),
+    "block_a_fullrow": (W_A, (0.5, -1, 4, -1, -1, False)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(BLOCK_CASES))
+def test_block_pruner_masks(name):
+    w, args = BLOCK_CASES[name]
+    cfg = BlockPrunerConfig(*args)
+    m = BlockPruner.generate_mask_by_pruning(w, cfg)
+    assert m.shape == w.shape and m.dtype == w.dtype
+    _same(name, m)
+    np.random.seed(77)
+    _same(name + "_static", BlockPruner.generate_mask_by_construction(w, cfg))
+
+
+def test_hb_grouping_masks():
+    hb = HbPrunerConfig([BlockPrunerConfig(0.875, 16, 8, -1, -1, False), BlockPrunerConfig(0.875, 1, 1, -1, -1, True)])
+    _same("hb_a", HbPruner.generate_mask(W_A, hb, False))
+    np.random.seed(78)
+    m = HbPruner.generate_mask(W_A, hb, True)
+    _same("hb_a_static", m)
+    assert m.max() == MASKS["hb_a_static_max"][0]
+    _same("group_a", GroupingPruner.construct_mask(W_A, GroupingPrunerConfig(4)))
+
+
+def test_rmb_rmcdb_masks():
+    _same("rmb_a", _quiet(RmbPruner.prune_tensor_as_rmb, W_A, RmbPrunerConfig(32, 72, 0.5, [BlockletType(8, 9)], [2])))
+    _same("rmb_b", _quiet(RmbPruner.prune_tensor_as_rmb, W_B,
+                          RmbPrunerConfig(16, 32, 0.5, [BlockletType(4, 4), BlockletType(2, 8)], [1, 1])))
+    _same("rmcdb_a", RmcdbPruner.prune_tensor_as_rmcdb(W_A, RmcdbPrunerConfig(32, 72, 0.5, [BlockletType(8, 9)], [2], True)))
+    _same("rmcdb_b", RmcdbPruner.prune_tensor_as_rmcdb(
+        W_B, RmcdbPrunerConfig(16, 32, 0.0, [BlockletType(4, 4), BlockletType(2, 8)], [1, 2], True)))
+    np.random.seed(79)
+    _same("rmcdb_a_static", RmcdbPruner.construct_rmcdb_matrix(
+        W_A, RmcdbPrunerConfig(32, 72, 0.0, [BlockletType(8, 9)], [2], True)))
+
+
+@pytest.mark.parametrize("pat", ["RANDOM", "UROW", "RAMANUJAN", "TRANS", "CDIA", "CDIASTRIDE", "COLUMN", "CBAND",
+                                 "CCDIA", "CCOLUMN", "GROUP"])
+def test_srmbrep_patterns(pat):
+    for rep in (True, False):
+        np.random.seed(80)
+        sq = pat == "TRANS"
+        cfg = SRMBRepMaskerConfig(32, 32 if sq else 16, 16, 16 if sq else 8, 1 if sq else 2, 1, 0.5, "UROW",
+                                  0.75, pat, rep, False, 0.5, False)
+        m = _quiet(SRMBRepMasker.construct_mask, np.zeros((64, 32, 3, 3), dtype=np.float32), cfg)
+        _same("srmb_%s_%d" % (pat, int(rep)), m)
+
+
+def test_srmbrep_special_cases_and_shipped_config():
+    np.random.seed(81)
+    cfg = SRMBRepMaskerConfig(-1, -1, 32, 32, 1, 1, 0.0, "UROW", 0.625, "TRANS", True, True, 0.5, False)
+    _same("srmb_trans_dense", SRMBRepMasker.construct_mask(np.zeros((32, 32, 1, 1), dtype=np.float32), cfg))
+    np.random.seed(82)
+    cfg = SRMBRepMaskerConfig(-1, -1, 16, 16, 1, 1, 0.0, "UROW", 0.5, "RAMANUJAN", True, True, 0.5, True)
+    _same("srmb_ramanujan_sym", SRMBRepMasker.construct_mask(np.zeros((32, 32, 1, 1), dtype=np.float32), cfg))
+    with open(golden("srmb_optimal_entry10.json")) as fh:
+        e = json.load(fh)
+    np.random.seed(83)
+    cfg = SRMBRepMaskerConfig(e["obh"], e["obw"], e["cbh"], e["cbw"], e["ibh"], e["ibw"], e["osp"], e["opat"],
+                              e["isp"], e["ipat"], e["is_repetitive"], e["collapse_tensor"], e["cross_prob"],
+                              e["is_symmetric"])
+    m = SRMBRepMasker.construct_mask(np.zeros(tuple(e["shape"]), dtype=np.float32), cfg)
+    _same("srmb_optimal_entry10", m)
+    assert abs(1 - np.count_nonzero(m) / m.size - 0.75) < 1e-6
+
+
+def test_pruner_objects_follow_the_reference_contract(tmp_path):
+    """config-file schema, mask_dict keys/shape/dtype, apply_masks in place, print_stats, type dispatch"""
+    model = drnb200.DRNSeg("drn_d_22", 19, pretrained=False)
+    shapes = collections.OrderedDict((k, tuple(v.shape)) for k, v in model.state_dict().items())
+    path = tmp_path / "block.json"
+    cfg = recipe.block_pruner_config(shapes, 0.75, str(path))
+    assert sum(len(c["layer_set"]) for c in cfg["configs"]) == 24
+    pruner = make_pruner(str(path), on_gpu=False)
+    assert isinstance(pruner, BlockPruner) and sorted(pruner.layer_configs) == sorted(recipe.prunable_keys(shapes))
+    pruner.generate_masks(model, is_static=False, verbose=False)
+    sd = model.state_dict()
+    for k, m in pruner.mask_dict.items():
+        assert m.shape == sd[k].shape and m.dtype == sd[k].dtype
+    before = sd["layer.6.0.conv2.weight"].clone()
+    pruner.apply_masks(model)
+    after = model.state_dict()["layer.6.0.conv2.weight"]
+    assert torch.equal(after, before * pruner.mask_dict["layer.6.0.conv2.weight"])
+    sp = pruner.sparsity()
+    assert abs(sp["layer.6.0.conv2.weight"] - 0.75) < 1e-9 and abs(sp["layer.8.0.weight"] - 0.75) < 1e-9
+    # fixture produced by the reference's BlockPruner on the same seeded weights
+    fx = np.load(golden("fwd_drn_d_22_64x128_block75.npz"))
+    sd2 = recipe.make_state_dict(load_keys("drn_d_22"), seed=int(fx["seed"]))
+    model.load_state_dict(sd2, strict=False)
+    pruner2 = make_pruner(str(path), on_gpu=False)
+    pruner2.generate_masks(model)
+    for k, m in pruner2.mask_dict.items():
+        assert np.array_equal(recipe.pack_mask_bits(m.numpy()), fx["maskbits:" + k]), k
+    for ptype, cls in (("hb", HbPruner), ("grouping", GroupingPruner), ("rmb", RmbPruner), ("rmcdb", RmcdbPruner),
+                       ("srmbrep", SRMBRepMasker)):
+        p = tmp_path / (ptype + ".json")
+        p.write_text(json.dumps({"pruner_type": ptype, "configs": []}))
+        assert isinstance(make_pruner(str(p), on_gpu=False), cls)
+    bad = tmp_path / "bad.json"
+    bad.write_text(json.dumps({"pruner_type": "nope", "configs": []}))
+    with pytest.raises(ValueError):
+        make_pruner(str(bad))
+
+
+def test_bsr_export_is_byte_identical(tmp_path):
+    fx = np.load(golden("bsr_case.npz"))
+    bm = BlockPruner.generate_block_matrix(fx["mat"], 4, 4)
+    out = tmp_path / "bsr.txt"
+    BlockPruner.write_block_matrix_to_file(bm, str(out))
+    assert out.read_text() == str(fx["text"])
+    back = BlockPruner.read_block_matrix_from_file(str(out))
+    assert np.array_equal(BlockPruner.block_matrix_to_dense(back), fx["mat"])
+    # the reference's own golden file round-trips through reader + exporter
+    ref = BlockPruner.read_block_matrix_from_file(golden("block_test.txt"))
+    dense = BlockPruner.block_matrix_to_dense(ref).astype(int)
+    out2 = tmp_path / "bt.txt"
+    BlockPruner.write_block_matrix_to_file(BlockPruner.generate_block_matrix(dense, 2, 2), str(out2))
+    assert out2.read_text() == open(golden("block_test.txt")).read()
+
+
+def test_shard_frames_partition():
+    for n in (0, 1, 7, 8, 25, 64):
+        for ws in (1, 2, 3, 8):
+            spans = [drnb200.shard_frames(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """no compute calls: the library must load on a GPU-less host and export what include/drnb200.h declares"""
+    header = open(os.path.join(ROOT, "include", "drnb200.h")).read()
+    declared = set(re.findall(r"\b(drnb200_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(ffi.SIGNATURES), declared ^ set(ffi.SIGNATURES)
+    assert os.path.exists(ffi.LIB_PATH), "build the library first: make -C video-seg-model-compress_b200/csrc"
+    handle = ctypes.CDLL(ffi.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    lib = ffi.lib()
+    assert lib.drnb200_version() == 100
+    # argument validation happens before any CUDA call, so it is testable here
+    assert lib.drnb200_compact_mask(None, 8, 8, 3, 3, 8, 8, None, None, None, None) == -1
+    assert b"null pointer" in lib.drnb200_last_error()

@@ -1,0 +1,13 @@
+"""drnb200 — B200-native inference path for block-pruned DRN semantic segmentation.
+
+Host-side mirror of the reference's two interfaces for this path (``DRNSeg`` of semantic_seg.py:126-164 and
+the ``pruners`` package) over the C-ABI library ``libdrnb200.so`` (include/drnb200.h).
+"""
+from . import ffi
+from .model import DRNSeg, fill_up_weights
+from . import drn
+from . import pruners
+from .evalops import ConfusionMeter, fast_hist, per_class_iu, shard_frames
+
+__all__ = ["DRNSeg", "fill_up_weights", "drn", "pruners", "ffi", "ConfusionMeter", "fast_hist",
+           "per_class_iu", "shard_frames"]
