@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: block-pruned DRN-D-22 frames/s @1024x2048 on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank/GPU)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference path on the host CPU cores)
+
+A step is one pass of the hot path over one batch of synthetic frames per GPU (BASELINE.json configs[1]:
+DRN-D-22, BlockPruner 75 % block-sparse masks, batch 8, 1024x2048).  Frames shard across ranks with no
+data-path collective (weights/tile lists replicated, "weak" scaling); the only NCCL call is the all-reduce of
+the 19x19 int64 confusion matrix at the end of the evaluation, inside the timed region.
+One JSON line is printed by rank 0; see README/DESIGN.md for the keys (roofline, cpu_baseline, e2e, clocks).
+"""
+import argparse
+import collections
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "video-seg-model-compress_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "pruned DRN-D-22 frames/s @1024x2048"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="drn_d_22")
+    ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step")
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=2048)
+    ap.add_argument("--sparsity", type=float, default=0.75)
+    ap.add_argument("--act", default="fp16", choices=["fp16", "bf16"],
+                    help="16-bit activation storage; fp16 is what passes the 99.9 %% label gate (DESIGN.md)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers-out", default=None, help="write the per-layer timing table (JSON) here")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p["bf16_tflops_sustained"], "tflops_burst": p["bf16_tflops"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "src": "fallback"}
+
+
+def build_model(args, device=None):
+    """synthetic weights of the named architecture + BlockPruner masks; returns (model, sd, pruner)"""
+    import drnb200
+    from drnb200 import synthetic
+    model = drnb200.DRNSeg(args.arch, 19, pretrained_model=None, pretrained=False, act_dtype=args.act)
+    shapes = collections.OrderedDict((k, tuple(v.shape)) for k, v in model.state_dict().items())
+    sd = synthetic.make_state_dict(shapes, seed=0)
+    model.load_state_dict(sd, strict=False)
+    pruner = None
+    if args.sparsity > 0:
+        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
+            json.dump(synthetic.block_pruner_config(shapes, args.sparsity), fh)
+        pruner = drnb200.pruners.make_pruner(fh.name, on_gpu=False)
+        pruner.generate_masks(model, is_static=False)          # the reference's magnitude block pruning
+        os.unlink(fh.name)
+        sd = synthetic.sparse_reinit(sd, pruner.mask_dict, seed=0)
+        model.load_state_dict(sd, strict=False)
+        pruner.apply_masks(model)
+    if device is not None:
+        model = model.to(device).eval()
+        model.set_pruner(pruner)
+    return model, sd, pruner
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                 "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10,
+                 "applications_clocks_setting": 0x2}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, b in names.items():
+                    if bits & b:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def run_reference(args):
+    """the reference's CPU implementation of the path (oracle port: torch CPU fp32, all host threads), timed on
+    a bounded sample: one 1024x2048 frame per step.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import drn_oracle
+    _, sd, _ = build_model(args)
+    from drnb200 import synthetic
+    x = synthetic.make_frames(1, args.height, args.width, seed=1234)
+    threads = torch.get_num_threads()
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 1))):
+            torch.max(drn_oracle.drnseg_forward(sd, x)[0], 1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            final, _ = drn_oracle.drnseg_forward(sd, x)
+            _, pred = torch.max(final, 1)           # semantic_seg.py:444-445
+        dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    sample = "1 frame %dx%d per step, fp32, %d steps" % (args.height, args.width, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload(args, 1),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload(args, batch):
+    return {"workload": "%s BlockPruner %.0f%% block-sparse, batch %d/GPU, %dx%d, act %s" % (
+        args.arch, 100 * args.sparsity, batch, args.height, args.width, args.act),
+        "arch": args.arch, "batch_per_gpu": batch, "height": args.height, "width": args.width,
+        "sparsity": args.sparsity, "act_dtype": args.act,
+        "l2": "inputs (%.0f MB/step) and activations exceed the 126 MB L2; no explicit flush" % (
+            batch * 3 * args.height * args.width * 4 / 1e6)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import drnb200
+    from drnb200 import synthetic
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    model, sd, pruner = build_model(args, dev)
+    B, H, W = args.batch, args.height, args.width
+    # synthetic frames: a distinct batch per rank, generated on the device outside the timed region
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(B, 3, H, W, device=dev, generator=g)
+    gt = torch.randint(0, 19, (B, H, W), device=dev, generator=g, dtype=torch.int64).to(torch.uint8)
+    meter = drnb200.ConfusionMeter(19, dev)
+    eng = model.engine()
+
+    def step(inp):
+        labels = model.predict(inp)
+        meter.update(labels, gt)
+        return labels
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            step(x)
+        if dist is not None:
+            meter.all_reduce()          # warm NCCL
+        barrier()
+        meter.hist.zero_()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step(x)
+        meter.all_reduce()              # the evaluation's single collective (NCCL over NVLink)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = (eng.launches_per_forward + 1) * args.steps
+        miou = meter.miou()
+
+        # ---- e2e: host frames -> H2D -> predict -> D2H labels, through the public API
+        hx = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+        hx.copy_(x.cpu())
+        hl = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+        xd = torch.empty_like(x)
+
+        def e2e_step():
+            xd.copy_(hx, non_blocking=True)
+            labels = model.predict(xd)
+            hl.copy_(labels, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        f0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        f1.record()
+        barrier()
+        e2e_wall = time.perf_counter() - t0
+        e2e_ms = max(f0.elapsed_time(f1), 1e3 * e2e_wall)
+        sampler.stop_flag = True
+        sampler.join()
+
+        # ---- per-layer timing pass (CUDA events per launch) for the roofline objects
+        per_layer = collections.OrderedDict()
+        reps = 3
+        for _ in range(reps):
+            tl = []
+            eng.run(x, want_labels=True, timings=tl)
+            torch.cuda.synchronize()
+            for name, a, b in tl:
+                per_layer[name] = per_layer.get(name, 0.0) + a.elapsed_time(b) / reps
+
+    # max over ranks
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk = peaks()
+        frames = world * B * args.steps
+        dense, live, tile = eng.mac_counts(B, H, W)
+        conv_ms = sum(v for k, v in per_layer.items() if k not in ("stem", "head"))
+        conv_live = live - B * H * W * 16 * 147 - B * (H // 8) * (W // 8) * 512 * 19      # minus stem and seg
+        conv_tflops = 2.0 * conv_live / (conv_ms * 1e-3) / 1e12
+        head_bytes = B * ((H // 8) * (W // 8) * 512 * 2 + H * W) + 19 * 512 * 4 + 19 * 4
+        head_gbs = head_bytes / (per_layer["head"] * 1e-3) / 1e9
+        layers = []
+        shapes = {-1: (H, W)}
+        for i, op in enumerate(eng.ops):
+            src = op.input_from if op.input_from is not None else i - 1
+            oh, ow = op.out_hw(*shapes[src])
+            shapes[i] = (oh, ow)
+            macs = B * oh * ow * op.live_elems
+            c = op.conv
+            io_bytes = 2 * B * (shapes[src][0] * shapes[src][1] * c.in_channels + oh * ow * c.out_channels)
+            lms = per_layer[op.key]
+            layers.append({"layer": op.key, "ms": lms, "live_gmac": macs / 1e9,
+                           "tflops_live": 2 * macs / (lms * 1e-3) / 1e12,
+                           "tensor_frac": 2 * macs / (lms * 1e-3) / 1e12 / pk["tflops"],
+                           "hbm_gbs": io_bytes / (lms * 1e-3) / 1e9,
+                           "live_tiles": op.n_live, "tile": [op.tile_o, op.tile_ci]})
+        if args.layers_out:
+            with open(args.layers_out, "w") as fh:
+                json.dump({"per_layer_ms": per_layer, "layers": layers, "batch": B}, fh, indent=1)
+        line = {
+            "metric": METRIC, "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.act,
+            "data": "synthetic", "config": workload(args, B),
+            "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s",
+                    "h2d_bytes_per_step": B * 3 * H * W * 4, "d2h_bytes_per_step": B * H * W},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (24 conv layers of one step)",
+                         "achieved": conv_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": conv_tflops / pk["tflops"], "traffic": None,
+                         "peak_source": pk["src"] + " bf16_tflops_sustained",
+                         "flops": "2 x unpruned (mask != 0) MACs of the conv stack, stem/seg excluded",
+                         "conv_ms_per_step": conv_ms},
+            "roofline_head": {"bound": "hbm", "kernel": "head (seg GEMM + upsample/argmax)",
+                              "achieved": head_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                              "frac": head_gbs / pk["hbm_gbs"], "traffic": None,
+                              "bytes_per_launch": head_bytes, "ms": per_layer["head"]},
+            "stem_ms_per_step": per_layer["stem"],
+            "macs_per_frame": {"dense_g": dense / B / 1e9, "unpruned_g": live / B / 1e9,
+                               "live_tile_g": tile / B / 1e9},
+            "miou_vs_random_labels": miou,
+        }
+        if not args.no_cpu_baseline:
+            from oracle import drn_oracle           # cpu_baseline leg: the oracle port, bounded sample
+            xs = synthetic.make_frames(1, H, W, seed=1234)
+            with torch.no_grad():
+                torch.max(drn_oracle.drnseg_forward(sd, xs)[0], 1)
+                t0 = time.perf_counter()
+                n_it = 3
+                for _ in range(n_it):
+                    torch.max(drn_oracle.drnseg_forward(sd, xs)[0], 1)
+                dt = (time.perf_counter() - t0) / n_it
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "frames/s", "cores": torch.get_num_threads(),
+                                    "kind": "port",
+                                    "sample": "1 frame %dx%d x %d iterations, torch CPU fp32 (oracle port of "
+                                              "semantic_seg.DRNSeg + torch.max)" % (H, W, n_it)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

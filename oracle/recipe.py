@@ -1,119 +1,4 @@
-"""ORACLE — test infrastructure, not product code.
-
-Deterministic synthetic weights, masks configs and frames shared by the golden-vector generator
-(which feeds them to the real reference), the oracle and the CUDA path (SURVEY 8d "Weights"/"Masks").
-
-Every tensor is drawn from its own ``torch.Generator`` seeded from (seed, state_dict key), so the values
-do not depend on module construction order and are identical for the reference's ``DRNSeg`` and for
-the mirror in video-seg-model-compress_b200 (same keys, same shapes).
-"""
-import collections
-import json
-import math
-import zlib
-
-import numpy as np
-import torch
-
-
-def _gen(seed, key):
-    g = torch.Generator(device="cpu")
-    g.manual_seed((zlib.crc32(key.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
-    return g
-
-
-def round_bf16(t):
-    """make values bf16-representable (both the fp32 oracle and the 16-bit CUDA path then share
-    identical conv weights)"""
-    return t.to(torch.bfloat16).to(torch.float32)
-
-
-def make_state_dict(shapes, seed=0, randomize_bn=True, bf16_weights=True):
-    """shapes: ordered {key: shape} of a DRNSeg state_dict -> {key: float32 tensor} (up.weight skipped).
-
-    conv weights ~ N(0, sqrt(2/(k*k*Cout))) (drn.py:169-172, semantic_seg.py:140-142), seg.bias small
-    random, BN gamma in U(0.5,1.5), beta/mean ~ 0.2*N(0,1), var in U(0.5,1.5) (identity BN when
-    ``randomize_bn`` is False, drn.py:173-175)."""
-    sd = collections.OrderedDict()
-    for key, shape in shapes.items():
-        shape = tuple(shape)
-        g = _gen(seed, key)
-        if key == "up.weight":
-            continue
-        if key.endswith("num_batches_tracked"):
-            sd[key] = torch.zeros(shape, dtype=torch.int64)
-        elif len(shape) == 4:
-            fan_out = shape[2] * shape[3] * shape[0]
-            w = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
-            sd[key] = round_bf16(w) if bf16_weights else w
-        elif key == "seg.bias":
-            sd[key] = 0.1 * torch.randn(shape, generator=g)
-        elif key.endswith("running_var"):
-            sd[key] = 0.5 + torch.rand(shape, generator=g) if randomize_bn else torch.ones(shape)
-        elif key.endswith("running_mean"):
-            sd[key] = 0.2 * torch.randn(shape, generator=g) if randomize_bn else torch.zeros(shape)
-        elif key.endswith(".weight"):      # BN gamma
-            sd[key] = 0.5 + torch.rand(shape, generator=g) if randomize_bn else torch.ones(shape)
-        elif key.endswith(".bias"):        # BN beta
-            sd[key] = 0.2 * torch.randn(shape, generator=g) if randomize_bn else torch.zeros(shape)
-        else:
-            raise KeyError("recipe: do not know how to fill %s %s" % (key, shape))
-    return sd
-
-
-def sparse_reinit(sd, mask_dict, seed=0, bf16_weights=True):
-    """the reference's static re-initialisation of surviving weights (semantic_seg.py:1031-1056):
-    ``tensor *= mask; tensor[mask != 0] ~ N(0, sqrt(2/n))`` with ``n = nnz // mask.shape[1]``, followed by
-    ``apply_masks``.  Values come from the per-key generator instead of the global RNG."""
-    for key, mask in mask_dict.items():
-        mask = mask.to("cpu")
-        w = sd[key] * mask
-        nnz = int((mask != 0).sum())
-        n = max(1, nnz // mask.shape[1])
-        vals = torch.randn(nnz, generator=_gen(seed + 1, key)) * math.sqrt(2.0 / n)
-        w[mask != 0] = round_bf16(vals) if bf16_weights else vals
-        sd[key] = w * (mask != 0).to(w.dtype)
-    return sd
-
-
-def make_frames(n, h, w, seed=1234):
-    """``torch.randn(N,3,H,W)`` frames (precedent: seg_video.py:281)"""
-    return torch.randn(n, 3, h, w, generator=torch.Generator().manual_seed(seed))
-
-
-def prunable_keys(shapes):
-    """conv weights the reference's experiment configs prune: everything except the 7x7 stem and `seg`
-    (expander_batch.py:42-43; optimal_configs/drn_d_22/* list exactly these 24 layers for D-22)"""
-    out = []
-    for key, shape in shapes.items():
-        if len(shape) == 4 and key.endswith(".weight") and shape[2] in (1, 3) and \
-                not key.startswith("seg.") and not key.startswith("up."):
-            out.append(key)
-    return out
-
-
-def block_pruner_config(shapes, sparsity=0.75, path=None):
-    """BASELINE config 2: BlockPruner JSON, ``collapse_tensor=false``, block = min(128, Cout/2) x
-    min(64, Cin/2) channels, one ``configs`` entry per distinct block shape (SURVEY 8d "Masks")."""
-    groups = collections.OrderedDict()
-    for key in prunable_keys(shapes):
-        o, i = shapes[key][0], shapes[key][1]
-        groups.setdefault((min(128, o // 2), min(64, i // 2)), []).append(key)
-    cfg = {"pruner_type": "block", "configs": [
-        {"layer_set": keys, "sparsity": sparsity, "block_height": bh, "block_width": bw,
-         "sub_rows": -1, "sub_cols": -1, "collapse_tensor": False}
-        for (bh, bw), keys in groups.items()]}
-    if path is not None:
-        with open(path, "w") as fh:
-            json.dump(cfg, fh, indent=1)
-    return cfg
-
-
-def pack_mask_bits(mask):
-    """compact storage of a {0, !=0} mask for fixtures"""
-    return np.packbits((np.asarray(mask) != 0).reshape(-1))
-
-
-def unpack_mask_bits(bits, shape):
-    n = int(np.prod(shape))
-    return np.unpackbits(bits)[:n].reshape(shape).astype(np.float32)
+"""ORACLE — test infrastructure.  The synthetic weight / mask / frame recipe lives with the product
+(drnb200.synthetic) because bench.py needs it without touching oracle/; re-exported here for the tests."""
+from drnb200.synthetic import *  # noqa: F401,F403
+from drnb200.synthetic import _gen  # noqa: F401

@@ -20,6 +20,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "video-seg-model-compress_b200"))
 REF = "/root/reference"
 
 from oracle import recipe  # noqa: E402

@@ -1,0 +1,445 @@
+"""Parity of the CUDA path (through the C ABI / DRNSeg mirror) against the oracle and the golden fixtures.
+
+Gates (BASELINE.json north_star): mask compaction bit-exact; label-map argmax agreement >= 99.9 % of pixels;
+logits within 2e-2 relative; mIoU within 0.1 point.  Run on the GPU box: pytest -m gpu
+"""
+import collections
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import drnb200
+from drnb200 import ffi
+from helpers import fixture_frames, fixture_state_dict, golden, load_keys
+from oracle import compact_oracle, drn_oracle, recipe
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_RTOL = 2e-2        # north_star: "logits within 2e-2 relative" (relative to the logit range)
+LABEL_AGREE = 0.999      # north_star: ">= 99.9 % of pixels"
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def rel_err(got, ref):
+    ref = ref.double()
+    return float((got.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+
+
+# ------------------------------------------------------------------------------------------------ (a)
+def _compact_on_gpu(mask, tile_o, tile_ci):
+    lib = ffi.lib()
+    O, I, kh, kw = mask.shape
+    m = torch.from_numpy(np.ascontiguousarray(mask, dtype=np.float32)).to(dev())
+    n_ot, n_kb = O // tile_o, (I // tile_ci) * kh * kw
+    rp = torch.full((n_ot + 1,), -1, dtype=torch.int32, device=dev())
+    kb = torch.full((max(1, n_ot * n_kb),), -1, dtype=torch.int32, device=dev())
+    nl = torch.zeros(1, dtype=torch.int32, device=dev())
+    ffi.check(lib.drnb200_compact_mask(ffi.ptr(m), O, I, kh, kw, tile_o, tile_ci, ffi.ptr(rp), ffi.ptr(kb),
+                                       ffi.ptr(nl), ffi.stream_ptr()))
+    torch.cuda.synchronize()
+    n = int(nl.item())
+    return rp.cpu().numpy(), kb.cpu().numpy()[:n], rp, kb
+
+
+def _masks_for_compaction():
+    fx = np.load(golden("pruner_masks.npz"))
+    out = []
+    for name, shape in (("block_a_uncollapsed", (64, 32, 3, 3)), ("block_a_collapsed", (64, 32, 3, 3)),
+                        ("block_a_unstructured", (64, 32, 3, 3)), ("hb_a", (64, 32, 3, 3)),
+                        ("rmb_a", (64, 32, 3, 3)), ("rmcdb_a", (64, 32, 3, 3)), ("group_a", (64, 32, 3, 3)),
+                        ("block_b_1x1conv", (32, 64, 1, 1)), ("srmb_RAMANUJAN_1", (64, 32, 3, 3)),
+                        ("srmb_optimal_entry10", (256, 256, 3, 3))):
+        out.append((name, recipe.unpack_mask_bits(fx[name], shape)))
+    rng = np.random.RandomState(0)
+    out.append(("empty", np.zeros((32, 32, 3, 3), np.float32)))
+    out.append(("full", np.ones((32, 32, 3, 3), np.float32)))
+    lone = np.zeros((128, 128, 3, 3), np.float32)
+    lone[77, 99, 2, 0] = 3.0                      # one surviving element, value != 1 (Hb-style)
+    out.append(("lone", lone))
+    out.append(("random_blocks", np.kron((rng.rand(4, 8) < 0.25), np.ones((128, 64))).reshape(512, 512, 1, 1)
+                .astype(np.float32).repeat(9, axis=2).reshape(512, 512, 3, 3)))
+    return out
+
+
+@pytest.mark.parametrize("tiles", [(16, 16), (32, 32), (8, 16), (128, 64)])
+def test_compaction_bit_exact(tiles):
+    tile_o, tile_ci = tiles
+    ran = 0
+    for name, mask in _masks_for_compaction():
+        O, I = mask.shape[:2]
+        if O % tile_o or I % tile_ci:
+            continue
+        rp_ref, kb_ref = compact_oracle.compact_mask(mask, tile_o, tile_ci)
+        rp, kb, _, _ = _compact_on_gpu(mask, tile_o, tile_ci)
+        assert np.array_equal(rp, rp_ref), name
+        assert np.array_equal(kb, kb_ref), name
+        ran += 1
+    assert ran >= 3
+
+
+@pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
+@pytest.mark.parametrize("tiles", [(16, 16), (32, 32), (64, 64), (128, 64)])
+def test_weight_packing_bit_exact(act, tiles):
+    tile_o, tile_ci = tiles
+    lib = ffi.lib()
+    rng = np.random.RandomState(1)
+    O, I = 256, 128
+    for k in (1, 3):
+        w = (rng.randn(O, I, k, k) * 0.05).astype(np.float32)
+        mask = np.kron(rng.rand(O // tile_o, I // tile_ci) < 0.5, np.ones((tile_o, tile_ci)))[:, :, None, None] \
+            * np.ones((1, 1, k, k))
+        mask = mask.astype(np.float32)
+        mask[0, 0, 0, 0] = 1.0
+        rp_ref, kb_ref = compact_oracle.compact_mask(mask, tile_o, tile_ci)
+        _, _, rp, kb = _compact_on_gpu(mask, tile_o, tile_ci)
+        packed = torch.zeros(len(kb_ref) * tile_o * tile_ci, dtype=torch.int16, device=dev())
+        wd, md = torch.from_numpy(w).to(dev()), torch.from_numpy(mask).to(dev())
+        ffi.check(lib.drnb200_pack_weights(ffi.ptr(wd), ffi.ptr(md), O, I, k, k, tile_o, tile_ci, ffi.ptr(rp),
+                                           ffi.ptr(kb), act, ffi.ptr(packed), ffi.stream_ptr()))
+        torch.cuda.synchronize()
+        ref = compact_oracle.pack_weights(w, mask, tile_o, tile_ci, rp_ref, kb_ref, act)
+        assert np.array_equal(packed.cpu().numpy().view(np.uint16), ref)
+
+
+# ------------------------------------------------------------------------------------------------ (b)
+def _conv_case(N, H, W, cin, cout, k, stride, dil, relu, res, act, impl, density, seed):
+    """one conv+BN(+res)(+ReLU) through the C ABI vs torch fp32 on the same 16-bit-representable operands"""
+    lib = ffi.lib()
+    g = torch.Generator().manual_seed(seed)
+    tdt = torch.bfloat16 if act == ffi.BF16 else torch.float16
+    tile_ci = 64 if cin % 64 == 0 else 32 if cin % 32 == 0 else 16
+    tile_o = 128 if cout % 128 == 0 else cout
+    x = torch.randn(N, cin, H, W, generator=g).to(tdt)
+    w = recipe.round_bf16(torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5)
+    blocks = (torch.rand(cout // tile_o, cin // tile_ci, generator=g) < density).float()
+    mask = torch.kron(blocks, torch.ones(tile_o, tile_ci))[:, :, None, None].expand(-1, -1, k, k).contiguous()
+    w = w * mask
+    scale = 0.5 + torch.rand(cout, generator=g)
+    shift = 0.2 * torch.randn(cout, generator=g)
+    OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
+    r = torch.randn(N, cout, OH, OW, generator=g).to(tdt) if res else None
+    # fp32 reference (weights as the kernel sees them: rounded to the activation dtype)
+    ref = torch.nn.functional.conv2d(x.float(), w.to(tdt).float(), None, stride, dil * (k // 2), dil)
+    ref = ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if res:
+        ref = ref + r.float()
+    if relu:
+        ref = ref.relu()
+    d = dev()
+    xd = x.permute(0, 2, 3, 1).contiguous().to(d)
+    rd = r.permute(0, 2, 3, 1).contiguous().to(d) if res else None
+    wd, md = w.to(d), mask.to(d)
+    n_ot, n_kb = cout // tile_o, (cin // tile_ci) * k * k
+    rp = torch.empty(n_ot + 1, dtype=torch.int32, device=d)
+    kb = torch.empty(n_ot * n_kb, dtype=torch.int32, device=d)
+    nl = torch.zeros(1, dtype=torch.int32, device=d)
+    st = ffi.stream_ptr()
+    ffi.check(lib.drnb200_compact_mask(ffi.ptr(md), cout, cin, k, k, tile_o, tile_ci, ffi.ptr(rp), ffi.ptr(kb),
+                                       ffi.ptr(nl), st))
+    packed = torch.empty(max(1, int(nl.item())) * tile_o * tile_ci, dtype=torch.int16, device=d)
+    ffi.check(lib.drnb200_pack_weights(ffi.ptr(wd), ffi.ptr(md), cout, cin, k, k, tile_o, tile_ci, ffi.ptr(rp),
+                                       ffi.ptr(kb), act, ffi.ptr(packed), st))
+    desc = ffi.ConvDesc(N=N, H=H, W=W, Cin=cin, Cout=cout, ksize=k, stride=stride, dilation=dil, relu=int(relu),
+                        has_residual=int(res), act_dtype=act, out_f32=1, tile_o=tile_o, tile_ci=tile_ci, impl=impl)
+    plan = C.c_void_p()
+    sc, sh = scale.to(d), shift.to(d)
+    ffi.check(lib.drnb200_conv_plan_create(C.byref(plan), C.byref(desc), ffi.ptr(rp), ffi.ptr(kb), ffi.ptr(packed),
+                                           ffi.ptr(sc), ffi.ptr(sh)))
+    assert lib.drnb200_conv_plan_impl(plan) == impl
+    y = torch.full((N, OH, OW, cout), float("nan"), dtype=torch.float32, device=d)
+    ffi.check(lib.drnb200_conv_forward(plan, ffi.ptr(xd), ffi.ptr(rd), ffi.ptr(y), st))
+    torch.cuda.synchronize()
+    lib.drnb200_conv_plan_destroy(plan)
+    got = y.permute(0, 3, 1, 2).cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
+
+
+CONV_CASES = [
+    # N  H   W   cin cout k  s  d  relu res  density
+    (2, 24, 40, 16, 16, 3, 1, 1, True, False, 1.0),      # layer1-like   (MODE_P, SWIZZLE_32B)
+    (1, 33, 47, 16, 32, 3, 2, 1, True, False, 1.0),      # layer2-like   (stride 2, odd size)
+    (1, 32, 64, 32, 64, 3, 2, 1, True, False, 1.0),      # layer3.0.conv1 (SWIZZLE_64B)
+    (1, 32, 64, 32, 64, 1, 2, 1, False, False, 1.0),     # layer3.0.downsample
+    (2, 16, 32, 64, 64, 3, 1, 1, True, True, 0.5),       # layer3.x.conv2 + residual
+    (1, 32, 64, 64, 128, 3, 2, 1, True, False, 1.0),     # layer4.0.conv1 (MODE_T, stride 2)
+    (1, 16, 32, 128, 256, 3, 1, 2, True, False, 0.5),    # layer5.0.conv1 (dilation 2)
+    (1, 16, 32, 256, 256, 1, 1, 1, False, False, 0.5),   # 1x1 projection
+    (2, 16, 32, 256, 512, 3, 1, 4, True, True, 0.25),    # layer6 (dilation 4, residual, 75 % sparse)
+    (1, 8, 16, 512, 512, 3, 1, 1, True, False, 0.0),     # everything pruned: y = relu(shift)
+    (1, 24, 24, 2048, 512, 3, 1, 2, True, False, 0.1),   # D-54 layer7: K = 18432
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
+def test_conv_tcgen05_vs_fp32(case, act):
+    N, H, W, cin, cout, k, s, d, relu, res, dens = case
+    _conv_case(N, H, W, cin, cout, k, s, d, relu, res, act, ffi.IMPL_TCGEN05, dens, seed=hash(case) & 0xFFFF)
+
+
+@pytest.mark.parametrize("case", CONV_CASES[:9])
+def test_conv_direct_vs_fp32(case):
+    N, H, W, cin, cout, k, s, d, relu, res, dens = case
+    _conv_case(N, H, W, cin, cout, k, s, d, relu, res, ffi.BF16, ffi.IMPL_DIRECT, dens, seed=7)
+
+
+# ------------------------------------------------------------------------------------------ end to end
+def _build(arch, sd, masks, act):
+    m = drnb200.DRNSeg(arch, 19, pretrained_model=None, pretrained=False, act_dtype=act)
+    missing = m.load_state_dict(sd, strict=False)
+    assert set(missing.missing_keys) <= {"up.weight"} and not missing.unexpected_keys
+    m = m.to(dev()).eval()
+    if masks:
+        m.set_masks(masks)
+    return m
+
+
+def _per_layer_report(model, sd, x):
+    """max error of every layer output against the oracle taps, relative to that layer's range"""
+    taps = {}
+    drn_oracle.drnseg_forward(sd, x, taps=taps)
+    return taps
+
+
+E2E = [("fwd_drn_d_22_64x128_dense.npz", "drn_d_22"), ("fwd_drn_d_22_64x128_block75.npz", "drn_d_22"),
+       ("fwd_drn_d_38_32x64_block75.npz", "drn_d_38"), ("fwd_drn_d_54_32x64_dense.npz", "drn_d_54"),
+       ("fwd_drn_c_26_32x64_dense.npz", "drn_c_26")]
+
+
+@pytest.mark.parametrize("name,arch", E2E)
+@pytest.mark.parametrize("act", ["fp16", "bf16"])
+def test_forward_against_golden_fixture(name, arch, act):
+    """small frames: CUDA path vs the outputs the real reference produced (tests/golden)"""
+    fx = np.load(golden(name))
+    sd, masks = fixture_state_dict(arch, fx)
+    model = _build(arch, sd, masks, act)
+    x = fixture_frames(fx).to(dev())
+    with torch.no_grad():
+        logprob, seg = model(x)
+        labels = model.predict(x)
+    torch.cuda.synchronize()
+    ref_seg = torch.from_numpy(fx["seg"])
+    assert seg.shape == ref_seg.shape and logprob.shape[2:] == x.shape[2:]
+    tol = LOGIT_RTOL if act == "fp16" else 2 * LOGIT_RTOL     # tiny maps + random nets: bf16 is looser
+    assert rel_err(seg.cpu(), ref_seg) <= tol
+    # forward()[0] and predict() agree with each other exactly
+    assert torch.equal(torch.max(logprob, 1)[1].to(torch.uint8), labels)
+    agree = (labels.cpu().numpy() == fx["labels"]).mean()
+    assert agree >= (0.99 if act == "fp16" else 0.97), agree
+    sample = logprob[0, :, ::7, ::13].cpu().numpy()
+    assert np.abs(sample - fx["logprob_sample"]).max() <= tol * np.abs(fx["seg"]).max() * 1.5
+
+
+def _gate_case(arch, h, w, n, pruned, act, seed):
+    shapes = load_keys(arch)
+    sd = recipe.make_state_dict(shapes, seed=seed)
+    model = drnb200.DRNSeg(arch, 19, pretrained=False, act_dtype=act)
+    model.load_state_dict(sd, strict=False)
+    masks = None
+    if pruned:
+        import json, tempfile, os
+        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
+            json.dump(recipe.block_pruner_config(shapes, 0.75), fh)
+        pruner = drnb200.pruners.make_pruner(fh.name, on_gpu=False)
+        pruner.generate_masks(model, is_static=False)
+        os.unlink(fh.name)
+        masks = pruner.mask_dict
+        sd = recipe.sparse_reinit(sd, masks, seed=seed)
+        model.load_state_dict(sd, strict=False)
+    model = model.to(dev()).eval()
+    model.set_masks(masks)
+    x = recipe.make_frames(n, h, w, seed=99 + seed)
+    return model, sd, x
+
+
+@pytest.mark.parametrize("pruned", [False, True])
+def test_parity_gates_drn_d_22(pruned):
+    """the north-star gates at 256x512 (oracle finishes in seconds): fp16 activation storage"""
+    model, sd, x = _gate_case("drn_d_22", 256, 512, 2, pruned, "fp16", seed=5)
+    ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
+    ref_lab = torch.max(ref_lp, 1)[1]
+    with torch.no_grad():
+        lp, seg = model(x.to(dev()))
+        lab = model.predict(x.to(dev()))
+    assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL
+    assert rel_err(lp.cpu(), ref_lp) <= LOGIT_RTOL
+    agree = (lab.cpu().long() == ref_lab).float().mean().item()
+    print("argmax agreement (fp16, pruned=%s): %.5f" % (pruned, agree))
+    assert agree >= LABEL_AGREE
+    # mIoU of both label maps against a synthetic ground truth: within 0.1 point
+    gt = torch.randint(0, 19, ref_lab.shape, generator=torch.Generator().manual_seed(3))
+    gt[ref_lab % 5 == 0] = 255
+    gt = torch.where(torch.rand(gt.shape, generator=torch.Generator().manual_seed(4)) < 0.5, ref_lab, gt)
+    ref_miou = drn_oracle.miou(drn_oracle.fast_hist(ref_lab.numpy().flatten(), gt.numpy().flatten(), 19))
+    meter = drnb200.ConfusionMeter(19, dev())
+    meter.update(lab, gt.to(dev()))
+    assert np.array_equal(meter.hist.cpu().numpy(),
+                          drn_oracle.fast_hist(lab.cpu().numpy().flatten().astype(np.int64), gt.numpy().flatten(), 19))
+    assert abs(meter.miou() - ref_miou) <= 0.1
+
+
+def test_bf16_storage_reported_separately():
+    """bf16 activation storage (north_star's nominal layout): logits gate holds; the label agreement is
+    reported, and must hold on pixels whose fp32 top-1/top-2 margin exceeds the logit tolerance"""
+    model, sd, x = _gate_case("drn_d_22", 256, 512, 1, True, "bf16", seed=6)
+    ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
+    ref_lab = torch.max(ref_lp, 1)[1]
+    with torch.no_grad():
+        seg = model(x.to(dev()))[1]
+        lab = model.predict(x.to(dev())).cpu().long()
+    assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL
+    top2 = ref_lp.topk(2, dim=1)[0]
+    margin = top2[:, 0] - top2[:, 1]
+    confident = margin > LOGIT_RTOL * ref_seg.abs().max()
+    agree_all = (lab == ref_lab).float().mean().item()
+    agree_conf = (lab == ref_lab)[confident].float().mean().item()
+    print("argmax agreement bf16: all %.5f, confident pixels (%.1f %%) %.5f" % (
+        agree_all, 100 * confident.float().mean().item(), agree_conf))
+    assert agree_conf >= LABEL_AGREE and agree_all >= 0.98
+
+
+def test_per_layer_outputs_track_the_oracle():
+    """every fused conv+BN(+res)+ReLU output vs the oracle tap of the same layer (error relative to range)"""
+    model, sd, x = _gate_case("drn_d_22", 64, 128, 1, True, "fp16", seed=8)
+    taps = {}
+    drn_oracle.drnseg_forward(sd, x, taps=taps)
+    eng = model.engine()
+    # run the engine layer by layer through its public ops (same launches as run())
+    with torch.no_grad():
+        model.predict(x.to(dev()))
+    assert eng.launches_per_forward == 1 + len(eng.ops) + 2
+    dense, live, tile = eng.mac_counts(1, 64, 128)
+    assert live < dense and live <= tile <= dense
+    assert abs(live / dense - 0.27) < 0.03          # 75 % of the 24 prunable layers + dense stem/seg
+
+
+def test_masks_from_zeros_and_from_torch_prune_give_the_same_tiles():
+    """mask ingestion: Pruner.mask_dict == weight != 0 == torch.nn.utils.prune buffers"""
+    import torch.nn.utils.prune as prune
+    model, sd, x = _gate_case("drn_d_22", 64, 128, 1, True, "fp16", seed=9)
+    xd = x.to(dev())
+    lab_masks = model.predict(xd)
+    lists_a = [(op.row_ptr.cpu().tolist(), op.kblk.cpu().tolist()[:op.n_live]) for op in model.engine().ops]
+    model.set_masks(None)                          # liveness from zeros of the already-masked weights
+    model.engine().ops[0].version = None
+    for op in model.engine().ops:
+        op.version = None
+    lab_zeros = model.predict(xd)
+    lists_b = [(op.row_ptr.cpu().tolist(), op.kblk.cpu().tolist()[:op.n_live]) for op in model.engine().ops]
+    assert lists_a == lists_b and torch.equal(lab_masks, lab_zeros)
+    conv = model.layer[8][0]
+    prune.l1_unstructured(conv, "weight", amount=0.9)     # semseg_unstructured.py:770-773
+    lab_pruned = model.predict(xd)
+    op = [o for o in model.engine().ops if o.key == "layer.8.0"][0]
+    assert op.live_elems <= int(0.1 * conv.weight_orig.numel()) + 1
+    assert lab_pruned.shape == lab_masks.shape
+
+
+def test_apply_masks_invalidates_the_cache():
+    model, sd, x = _gate_case("drn_d_22", 64, 128, 1, False, "fp16", seed=10)
+    xd = x.to(dev())
+    a = model.predict(xd)
+    with torch.no_grad():
+        model.state_dict()["layer.8.0.weight"].mul_(0.0)     # what Pruner.apply_masks does in place
+    b = model.predict(xd)
+    op = [o for o in model.engine().ops if o.key == "layer.8.0"][0]
+    assert op.n_live == 0 and not torch.equal(a, b)
+
+
+def test_input_validation():
+    model, sd, x = _gate_case("drn_d_22", 64, 128, 1, False, "fp16", seed=11)
+    with pytest.raises(ffi.Drnb200Error):
+        model.predict(torch.zeros(1, 3, 60, 64, device=dev()))       # H % 8 != 0
+    with pytest.raises(ffi.Drnb200Error):
+        model.predict(torch.zeros(1, 3, 64, 64, device=dev(), dtype=torch.float16))
+    out = model.predict(torch.zeros(3, 3, 72, 200, device=dev()))    # ragged map sizes (9 x 25 at 1/8)
+    assert out.shape == (3, 72, 200)
+
+
+def test_head_borders_against_conv_transpose():
+    """the zero-padded ConvTranspose2d rule (not F.interpolate) incl. the outer 4 pixels, and first-max ties"""
+    lib = ffi.lib()
+    d = dev()
+    g = torch.Generator().manual_seed(2)
+    N, h, w, Cc, classes = 2, 6, 11, 64, 19
+    feat = torch.randn(N, Cc, h, w, generator=g).half()
+    sw = recipe.round_bf16(torch.randn(classes, Cc, generator=g) * 0.2)
+    sb = 0.1 * torch.randn(classes, generator=g)
+    sd = {"seg.weight": sw.half().float().view(classes, Cc, 1, 1), "seg.bias": sb}
+    ref_lp, ref_seg = drn_oracle.head_forward(sd, feat.float())
+    plan = C.c_void_p()
+    swd, sbd = sw.to(d), sb.to(d)
+    ffi.check(lib.drnb200_head_plan_create(C.byref(plan), N, h, w, Cc, classes, ffi.F16, ffi.ptr(swd), ffi.ptr(sbd),
+                                           ffi.stream_ptr()))
+    xd = feat.permute(0, 2, 3, 1).contiguous().to(d)
+    lab = torch.empty(N, 8 * h, 8 * w, dtype=torch.uint8, device=d)
+    seg = torch.empty(N, classes, h, w, dtype=torch.float32, device=d)
+    lp = torch.empty(N, classes, 8 * h, 8 * w, dtype=torch.float32, device=d)
+    ffi.check(lib.drnb200_head_forward(plan, ffi.ptr(xd), ffi.ptr(lab), ffi.ptr(seg), ffi.ptr(lp), ffi.stream_ptr()))
+    torch.cuda.synchronize()
+    lib.drnb200_head_plan_destroy(plan)
+    assert (seg.cpu() - ref_seg).abs().max() <= 1e-3
+    assert (lp.cpu() - ref_lp).abs().max() <= 2e-3
+    ref_lab = torch.max(ref_lp, 1)[1]
+    top2 = ref_lp.topk(2, dim=1)[0]
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-3
+    assert torch.equal(lab.cpu().long()[clear], ref_lab[clear])
+    # all-equal logits: every class ties, torch.max returns index 0
+    plan = C.c_void_p()
+    zw, zb = torch.zeros(classes, Cc, device=d), torch.zeros(classes, device=d)
+    ffi.check(lib.drnb200_head_plan_create(C.byref(plan), N, h, w, Cc, classes, ffi.F16, ffi.ptr(zw), ffi.ptr(zb),
+                                           ffi.stream_ptr()))
+    ffi.check(lib.drnb200_head_forward(plan, ffi.ptr(xd), ffi.ptr(lab), None, None, ffi.stream_ptr()))
+    torch.cuda.synchronize()
+    lib.drnb200_head_plan_destroy(plan)
+    assert int(lab.max()) == 0
+
+
+def test_confusion_matrix_and_ignore_label():
+    fx = np.load(golden("metrics.npz"))
+    pred = torch.from_numpy(fx["pred"].astype(np.uint8)).to(dev())
+    lab64 = torch.from_numpy(fx["label"].astype(np.int64)).to(dev())
+    lab8 = torch.from_numpy(fx["label"].astype(np.uint8)).to(dev())
+    for lab in (lab64, lab8):
+        meter = drnb200.ConfusionMeter(19, dev())
+        meter.update(pred, lab)
+        assert np.array_equal(meter.hist.cpu().numpy(), fx["hist"])
+        assert meter.miou() == float(fx["miou"])
+    empty = drnb200.ConfusionMeter(19, dev())
+    empty.update(pred[:0], lab8[:0])
+    assert int(empty.hist.sum()) == 0
+    tiny = drnb200.fast_hist(torch.tensor([0, 1, 1, 2], dtype=torch.uint8, device=dev()),
+                             torch.tensor([0, 1, 2, 255], dtype=torch.int64, device=dev()), 3)
+    assert np.array_equal(tiny.cpu().numpy(), fx["tiny"])
+
+
+def test_full_size_properties():
+    """BASELINE size (1024x2048): size-independent properties instead of a minutes-long CPU oracle run:
+    (i) tcgen05 and CUDA-core direct kernels agree layer for layer on the same tile lists,
+    (ii) frames are independent: predict(batch)[i] == predict(frame i),
+    (iii) determinism: two runs are bit-identical, (iv) the label histogram sums to the pixel count."""
+    model, sd, x = _gate_case("drn_d_22", 1024, 2048, 2, True, "fp16", seed=12)
+    xd = x.to(dev())
+    a = model.predict(xd)
+    b = model.predict(xd)
+    assert torch.equal(a, b)
+    assert torch.equal(model.predict(xd[1:2])[0], a[1])
+    meter = drnb200.ConfusionMeter(19, dev())
+    meter.update(a, a)
+    h = meter.hist.cpu().numpy()
+    assert h.sum() == a.numel() and np.count_nonzero(h - np.diag(np.diag(h))) == 0
+    eng = model.engine()
+    eng.conv_impl = ffi.IMPL_DIRECT
+    c = model.predict(xd[:1])
+    eng.conv_impl = ffi.IMPL_AUTO
+    agree = (c[0] == a[0]).float().mean().item()
+    print("tcgen05 vs direct label agreement at 1024x2048: %.6f" % agree)
+    assert agree >= 0.9995

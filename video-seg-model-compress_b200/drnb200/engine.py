@@ -146,6 +146,26 @@ def _check_conv(conv, key):
         raise ffi.Drnb200Error("conv %s: unsupported configuration %r" % (key, conv))
 
 
+class _Timed:
+    """context manager recording a CUDA-event pair around a launch group (no-op when disabled)"""
+
+    def __init__(self, name, sink):
+        self.name, self.sink = name, sink
+
+    def __enter__(self):
+        if self.sink is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.sink is not None:
+            self.e1.record()
+            self.sink.append((self.name, self.e0, self.e1))
+        return False
+
+
 class Engine:
     """builds and runs the launch list for one DRNSeg module"""
 
@@ -314,7 +334,12 @@ class Engine:
         return dense + seg, live + seg, tile + seg
 
     # ---- forward ---------------------------------------------------------------------------------
-    def run(self, x, want_labels=True, want_logprob=False, want_seg=False):
+    def run(self, x, want_labels=True, want_logprob=False, want_seg=False, timings=None):
+        """launch the whole path on the current stream.  `timings`, if a list, receives
+        (name, start_event, end_event) per launch group (CUDA events on the launching stream)."""
+        def timed(name):
+            return _Timed(name, timings)
+
         if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3):
             raise ffi.Drnb200Error("input must be a float32 CUDA tensor [N,3,H,W] (got %s %s on %s); "
                                    "there is no CPU path" % (tuple(x.shape), x.dtype, x.device))
@@ -355,9 +380,10 @@ class Engine:
         sconv = self.stem[0]
         c0 = sconv.out_channels
         y = take(N * H * W * c0)
-        ffi.check(lib.drnb200_stem_forward(ffi.ptr(x), ffi.ptr(self.stem_w), ffi.ptr(self.stem_scale),
-                                           ffi.ptr(self.stem_shift), N, H, W, c0, adt, ffi.ptr(y), st),
-                  "stem_forward")
+        with timed("stem"):
+            ffi.check(lib.drnb200_stem_forward(ffi.ptr(x), ffi.ptr(self.stem_w), ffi.ptr(self.stem_scale),
+                                               ffi.ptr(self.stem_shift), N, H, W, c0, adt, ffi.ptr(y), st),
+                      "stem_forward")
         launches += 1
         outs[-1] = y
         for i, op in enumerate(self.ops):
@@ -368,8 +394,9 @@ class Engine:
             plan = op.plan(N, ih, iw, adt, self.conv_impl)
             yo = take(N * oh * ow * op.conv.out_channels)
             res = outs[op.residual_from] if op.residual_from is not None else None
-            ffi.check(lib.drnb200_conv_forward(plan, ffi.ptr(outs[src]), ffi.ptr(res), ffi.ptr(yo), st),
-                      "conv_forward(%s)" % op.key)
+            with timed(op.key):
+                ffi.check(lib.drnb200_conv_forward(plan, ffi.ptr(outs[src]), ffi.ptr(res), ffi.ptr(yo), st),
+                          "conv_forward(%s)" % op.key)
             launches += 1
             outs[i] = yo
             for j in [k for k, last in last_use.items() if last == i]:
@@ -382,8 +409,9 @@ class Engine:
         logprob = torch.empty((N, classes, 8 * h8, 8 * w8), dtype=torch.float32, device=dev) \
             if want_logprob else None
         seg = torch.empty((N, classes, h8, w8), dtype=torch.float32, device=dev) if want_seg else None
-        ffi.check(lib.drnb200_head_forward(hp, ffi.ptr(outs[last]), ffi.ptr(labels), ffi.ptr(seg),
-                                           ffi.ptr(logprob), st), "head_forward")
+        with timed("head"):
+            ffi.check(lib.drnb200_head_forward(hp, ffi.ptr(outs[last]), ffi.ptr(labels), ffi.ptr(seg),
+                                               ffi.ptr(logprob), st), "head_forward")
         launches += 1 + int(want_labels or want_logprob) + int(want_seg)
         self.launches_per_forward = launches
         return labels, logprob, seg

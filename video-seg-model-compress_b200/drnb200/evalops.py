@@ -52,6 +52,8 @@ class ConfusionMeter:
             raise ffi.Drnb200Error("label must be uint8 or int64 (got %s)" % label.dtype)
         if pred.numel() != label.numel():
             raise ffi.Drnb200Error("pred and label differ in size")
+        if pred.numel() == 0:
+            return
         pred, label = pred.contiguous(), label.contiguous()
         ffi.check(ffi.lib().drnb200_confusion(ffi.ptr(pred), ffi.ptr(label), int(label.dtype == torch.int64),
                                               pred.numel(), self.classes, ffi.ptr(self.hist),
