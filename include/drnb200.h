@@ -114,7 +114,19 @@ void drnb200_conv_plan_destroy(drnb200_conv_plan* plan);
 
 /* Stem: nn.Conv2d(3,C0,7,stride 1,pad 3) -> BatchNorm2d -> ReLU (drn.py:132-137).
  * x: float32 NCHW [N,3,H,W] exactly as the callers feed DRNSeg.forward (semantic_seg.py:444);
- * w: float32 OIHW [C0,3,7,7]; y: act_dtype NHWC [N,H,W,C0].  C0 must be 16. */
+ * w: float32 OIHW [C0,3,7,7]; y: act_dtype NHWC [N,H,W,C0].  C0 must be 16.
+ * Two implementations:
+ *   drnb200_stem_plan_*    tcgen05: the 128-pixel x 160 im2col tile is gathered from the fp32 frame,
+ *                          converted to act_dtype and multiplied on the tensor cores (weights rounded to
+ *                          act_dtype once at plan creation); this is what DRNSeg uses.
+ *   drnb200_stem_forward   CUDA-core fp32 direct convolution (no input/weight rounding); kept as the
+ *                          full-precision cross-check of the tensor-core stem. */
+typedef struct drnb200_stem_plan drnb200_stem_plan;
+int  drnb200_stem_plan_create(drnb200_stem_plan** out, const float* w_oihw, const float* bn_scale,
+                              const float* bn_shift, int N, int H, int W, int C0, int act_dtype,
+                              void* stream);
+int  drnb200_stem_plan_forward(drnb200_stem_plan* plan, const float* x_nchw, void* y_nhwc, void* stream);
+void drnb200_stem_plan_destroy(drnb200_stem_plan* plan);
 int drnb200_stem_forward(const float* x_nchw, const float* w_oihw, const float* bn_scale,
                          const float* bn_shift, int N, int H, int W, int C0, int act_dtype,
                          void* y_nhwc, void* stream);

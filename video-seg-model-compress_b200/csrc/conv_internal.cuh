@@ -27,6 +27,8 @@ struct ConvParams {
   int stages;
   uint32_t idesc;
   uint32_t w_tile_bytes, x_tile_bytes, w_stage_bytes, stage_bytes, pitch;
+  // ---- staged epilogue (MODE_T, 16-bit output): 32-pixel x 128-cout chunks through shared memory + TMA
+  int ep_cw, ep_ch, ep_nch;   // chunk box (pixels wide x high), chunks per tile
 };
 
 }  // namespace drnb200
@@ -42,6 +44,9 @@ struct drnb200_conv_plan {
   int32_t* d_ot_order;
   CUtensorMap tmap;        // activations, bound to `tmap_ptr`
   const void* tmap_ptr;
+  CUtensorMap tmap_y, tmap_r;   // output / residual chunk boxes (staged epilogue), bound to the pointers below
+  const void* tmap_y_ptr;
+  const void* tmap_r_ptr;
   std::vector<int32_t> h_row_ptr;
 };
 
@@ -49,4 +54,7 @@ namespace drnb200 {
 int conv_direct_launch(const drnb200_conv_plan* plan, cudaStream_t st);
 int conv_tc_setup(drnb200_conv_plan* plan);                 // decide tile shapes, smem, attributes
 int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st);
+bool conv_gather_supported(const drnb200_conv_desc& d);     // 16-channel 3x3 layers (conv_gather.cu)
+int conv_gather_launch(drnb200_conv_plan* plan, cudaStream_t st);
+constexpr int TC_MODE_GATHER = 3;
 }  // namespace drnb200

@@ -30,6 +30,8 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
   plan->d = d;
   plan->d_ot_order = nullptr;
   plan->tmap_ptr = nullptr;
+  plan->tmap_y_ptr = nullptr;
+  plan->tmap_r_ptr = nullptr;
   ConvParams& p = plan->p;
   p = ConvParams{};
   p.row_ptr = row_ptr; p.kblk = kblk; p.w_packed = reinterpret_cast<const uint8_t*>(w_packed);
@@ -50,7 +52,10 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
   plan->tile_macs = n_live * (int64_t)p.tile_o * p.tile_ci * (int64_t)p.N * p.OH * p.OW;
 
   plan->impl = 0;
-  if (d.impl != DRNB200_IMPL_DIRECT) {
+  if (d.impl != DRNB200_IMPL_DIRECT && conv_gather_supported(d)) {
+    plan->impl = DRNB200_IMPL_TCGEN05;
+    plan->tc_mode = TC_MODE_GATHER;
+  } else if (d.impl != DRNB200_IMPL_DIRECT) {
     int rc = conv_tc_setup(plan);
     if (rc == DRNB200_OK) plan->impl = DRNB200_IMPL_TCGEN05;
     else if (d.impl == DRNB200_IMPL_TCGEN05 || rc != DRNB200_E_ARG) {
@@ -81,7 +86,8 @@ extern "C" int drnb200_conv_forward(drnb200_conv_plan* plan, const void* x_nhwc,
   plan->p.residual = plan->d.has_residual ? residual_or_null : nullptr;
   plan->p.y = y_nhwc;
   cudaStream_t st = (cudaStream_t)stream;
-  return plan->impl == DRNB200_IMPL_TCGEN05 ? conv_tc_launch(plan, st) : conv_direct_launch(plan, st);
+  if (plan->impl != DRNB200_IMPL_TCGEN05) return conv_direct_launch(plan, st);
+  return plan->tc_mode == TC_MODE_GATHER ? conv_gather_launch(plan, st) : conv_tc_launch(plan, st);
 }
 
 extern "C" int drnb200_conv_plan_impl(const drnb200_conv_plan* plan) { return plan ? plan->impl : 0; }

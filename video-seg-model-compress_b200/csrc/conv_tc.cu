@@ -17,6 +17,11 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2-5 = epilogue (TMEM -> registers -> BN affine (+residual) (+ReLU) -> NHWC global).
 // Two accumulator stages in TMEM (2 x 256 columns) let the epilogue of tile i overlap the MMAs of i+1.
+// MODE_T epilogue ("staged"): the accumulator is cout-major (lane = cout) but the output is NHWC, so
+// each 32-pixel x 128-cout chunk is transposed through a ring of four 8 KB shared-memory buffers:
+// the residual chunk arrives there by TMA (prefetched one chunk ahead), every thread fuses
+// BN affine + residual + ReLU in place (2-byte accesses, 64 contiguous bytes per warp: conflict-free),
+// and one TMA store per chunk writes full 256-byte pixel rows (out-of-image pixels are clipped by TMA).
 #include "conv_internal.cuh"
 #include <algorithm>
 #include <cudaTypedefs.h>
@@ -25,15 +30,20 @@ namespace drnb200 {
 
 constexpr int kTcThreads = 192;
 constexpr int kMaxStages = 8;
-constexpr int MODE_T = 0;
+constexpr int MODE_T = 0;      // staged epilogue (16-bit output)
 constexpr int MODE_P = 1;
+constexpr int MODE_TD = 2;     // MODE_T with the direct (register -> global) epilogue: float32 output
 constexpr uint32_t kTmemCols = 512;
+constexpr int kEpRing = 4;     // staging buffers of the MODE_T epilogue
+constexpr int kEpChunkPx = 32; // pixels per staged chunk (one tcgen05.ld.32x32b.x32 per warp)
+constexpr int kEpBufBytes = kEpChunkPx * 256;
 
 struct __align__(8) TcSync {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tfull[2];
   uint64_t tempty[2];
+  uint64_t rfull[kEpRing];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -66,18 +76,25 @@ __device__ __forceinline__ float finish(float acc, float sc, float sh, float res
 
 template <int MODE, int DT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y,
+               const __grid_constant__ CUtensorMap tmap_r, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // tiles must sit on 1024-byte boundaries of the shared window (SWIZZLE_128B atom)
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  TcSync* sync = reinterpret_cast<TcSync*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint8_t* stg = smem + (size_t)p.stages * p.stage_bytes;            // MODE_T staging ring
+  TcSync* sync = reinterpret_cast<TcSync*>(stg + (MODE == MODE_T ? kEpRing * kEpBufBytes : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap);
+    if (MODE == MODE_T) {
+      tma_prefetch_desc(&tmap_y);
+      if (p.has_res) tma_prefetch_desc(&tmap_r);
+    }
+    for (int b = 0; b < kEpRing; ++b) mbar_init(&sync->rfull[b], 1);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&sync->full[s], 1);
       mbar_init(&sync->empty[s], 1);
@@ -144,7 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
           const uint64_t dX = umma_smem_desc(sX, p.pitch);
           for (int i = 0; i < ksteps; ++i) {
             const uint32_t accum = (j > c.jb || i > 0) ? 1u : 0u;
-            if (MODE == MODE_T)
+            if (MODE != MODE_P)
               umma_f16(d_tmem, dW + (uint64_t)(2 * i), dX + (uint64_t)(2 * i), p.idesc, accum);
             else
               umma_f16(d_tmem, dX + (uint64_t)(2 * i), dW + (uint64_t)(2 * i), p.idesc, accum);
@@ -165,6 +182,92 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     const uint16_t* res16 = reinterpret_cast<const uint16_t*>(p.residual);
     uint16_t* y16 = reinterpret_cast<uint16_t*>(p.y);
     float* y32 = reinterpret_cast<float*>(p.y);
+
+    if (MODE == MODE_T) {
+      // ------------------------------------------------ staged: smem transpose + TMA load/store
+      const bool leader = (warp == 2 && lane == 0);       // issues every TMA of the epilogue
+      const int cl = q * 32 + lane;                       // cout inside the 128-cout tile
+      const int nch = p.ep_nch;
+      uint32_t k = 0;                                     // flat chunk counter (ring position)
+      auto chunk_xy = [&](const TileCoord& c, int qq, int& cx, int& cy) {
+        const int j0 = qq * kEpChunkPx;
+        cx = c.ox0 + (j0 & (p.TW - 1));
+        cy = c.oy0 + (j0 >> p.tw_shift);
+      };
+      if (leader && p.has_res && (int)blockIdx.x < p.total_tiles) {   // residual of the very first chunk
+        const TileCoord c0 = decode_tile(p, blockIdx.x);
+        int cx, cy;
+        chunk_xy(c0, 0, cx, cy);
+        mbar_arrive_expect_tx(&sync->rfull[0], kEpBufBytes);
+        tma_load_4d(&tmap_r, &sync->rfull[0], stg, c0.ot * 128, cx, cy, c0.n);
+      }
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        const bool live = c.je > c.jb;
+        const int co = c.ot * 128 + cl;
+        const float sc = __ldg(p.scale + co), sh = __ldg(p.shift + co);
+        if (live) {
+          mbar_wait(&sync->tfull[acc], acc_phase);
+          tc_fence_after();
+        }
+        const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
+        for (int qq = 0; qq < nch; ++qq, ++k) {
+          const uint32_t b = k & (kEpRing - 1);
+          uint8_t* buf = stg + b * kEpBufBytes;
+          if (leader) {
+            // stores k-1 and k-2 may still be reading their buffers; k-3 (the previous user of ring
+            // slot (k+1)%4) is done, so the next chunk's residual can land there
+            bulk_wait_group_read<2>();
+            if (p.has_res) {
+              int nt = t, nq = qq + 1;
+              if (nq == nch) { nq = 0; nt = t + gridDim.x; }
+              if (nt < p.total_tiles) {
+                const TileCoord cn = (nt == t) ? c : decode_tile(p, nt);
+                int cx, cy;
+                chunk_xy(cn, nq, cx, cy);
+                const uint32_t nb = (k + 1) & (kEpRing - 1);
+                mbar_arrive_expect_tx(&sync->rfull[nb], kEpBufBytes);
+                tma_load_4d(&tmap_r, &sync->rfull[nb], stg + nb * kEpBufBytes, cn.ot * 128, cx, cy, cn.n);
+              }
+            }
+          }
+          named_bar_sync(1, 128);                          // ring slot b is free for this chunk
+          if (p.has_res) mbar_wait(&sync->rfull[b], (k / kEpRing) & 1u);
+          uint32_t v[32];
+          if (live) {
+            tmem_ld32(t_addr + (uint32_t)(qq * kEpChunkPx), v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
+          uint16_t* col = reinterpret_cast<uint16_t*>(buf) + cl;   // [pixel][128 couts]
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float r = p.has_res ? Act<DT>::to_f32(col[i * 128]) : 0.f;
+            col[i * 128] = Act<DT>::from_f32(finish<DT>(__uint_as_float(v[i]), sc, sh, r, p.relu));
+          }
+          if (live && qq == nch - 1) {                     // accumulator fully read: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sync->tempty[acc]);
+          }
+          fence_proxy_async_smem();                        // st.shared -> visible to the TMA store
+          named_bar_sync(2, 128);
+          if (leader) {
+            int cx, cy;
+            chunk_xy(c, qq, cx, cy);
+            tma_store_4d(&tmap_y, buf, c.ot * 128, cx, cy, c.n);
+            bulk_commit_group();
+          }
+        }
+        if (live) {
+          acc ^= 1u;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+      if (leader) bulk_wait_group<0>();                    // all stores complete before the CTA retires
+    } else {
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord c = decode_tile(p, t);
       const bool live = c.je > c.jb;
@@ -174,8 +277,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
       }
       const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
 
-      if (MODE == MODE_T) {
-        // lane = output channel, columns = pixels of the tile
+      if (MODE == MODE_TD) {
+        // lane = output channel, columns = pixels of the tile; direct 2/4-byte global accesses
         const int co = c.ot * 128 + q * 32 + lane;
         const float sc = __ldg(p.scale + co), sh = __ldg(p.shift + co);
         const int nt = p.TW * p.TH;
@@ -263,6 +366,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         if (acc == 0) acc_phase ^= 1u;
       }
     }
+    }
   }
 
   // ------------------------------------------------------------------------- teardown
@@ -315,7 +419,7 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   const bool k_ok = (d.ksize == 1 || d.ksize == 3) && (d.stride == 1 || d.stride == 2);
   int mode = -1;
   if (ci_ok && k_ok) {
-    if (p.tile_o == 128 && p.Cout % 128 == 0) mode = MODE_T;
+    if (p.tile_o == 128 && p.Cout % 128 == 0) mode = d.out_f32 ? MODE_TD : MODE_T;
     else if (p.tile_o == p.Cout && p.Cout % 16 == 0 && p.Cout <= 256) mode = MODE_P;
   }
   if (mode < 0) {
@@ -325,7 +429,7 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   }
   plan->tc_mode = mode;
   // ---- pixel tile
-  const int nt_max = (mode == MODE_T) ? 256 : 128;
+  const int nt_max = (mode != MODE_P) ? 256 : 128;
   int TW = std::min(std::min(pow2_ceil(p.OW), nt_max), 256 / d.stride);
   int TH = std::min(pow2_ceil(p.OH), nt_max / TW);
   if (mode == MODE_P) TH = 128 / TW;           // UMMA M is exactly 128 pixels
@@ -345,11 +449,15 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   p.x_tile_bytes = (uint32_t)NT * p.pitch;
   p.w_stage_bytes = (p.w_tile_bytes + 1023u) & ~1023u;
   p.stage_bytes = p.w_stage_bytes + ((p.x_tile_bytes + 1023u) & ~1023u);
-  p.idesc = (mode == MODE_T) ? umma_idesc_f16(128, NT, d.act_dtype)
+  p.idesc = (mode != MODE_P) ? umma_idesc_f16(128, NT, d.act_dtype)
                              : umma_idesc_f16(128, p.Cout, d.act_dtype);
+  // staged epilogue geometry: chunks of 32 consecutive tile pixels = a box of ep_cw x ep_ch pixels
+  p.ep_cw = std::min(TW, kEpChunkPx);
+  p.ep_ch = kEpChunkPx / p.ep_cw;
+  p.ep_nch = NT / kEpChunkPx;
   // ---- shared memory: as many stages as fit in 227 KB (also pins one CTA per SM: TMEM is taken whole)
   const size_t kMaxSmem = 232448;
-  const size_t fixed = 1024 + sizeof(TcSync);
+  const size_t fixed = 1024 + sizeof(TcSync) + (mode == MODE_T ? kEpRing * kEpBufBytes : 0);
   int stages = (int)((kMaxSmem - fixed) / p.stage_bytes);
   stages = std::max(2, std::min(stages, kMaxStages));
   p.stages = stages;
@@ -358,6 +466,9 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   if (mode == MODE_T)
     rc = (d.act_dtype == DRNB200_BF16) ? set_attr<MODE_T, DRNB200_BF16>(plan->smem_bytes)
                                        : set_attr<MODE_T, DRNB200_F16>(plan->smem_bytes);
+  else if (mode == MODE_TD)
+    rc = (d.act_dtype == DRNB200_BF16) ? set_attr<MODE_TD, DRNB200_BF16>(plan->smem_bytes)
+                                       : set_attr<MODE_TD, DRNB200_F16>(plan->smem_bytes);
   else
     rc = (d.act_dtype == DRNB200_BF16) ? set_attr<MODE_P, DRNB200_BF16>(plan->smem_bytes)
                                        : set_attr<MODE_P, DRNB200_F16>(plan->smem_bytes);
@@ -379,6 +490,34 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   plan->grid = std::min(p.total_tiles, sms);
   plan->tmap_ptr = nullptr;
+  plan->tmap_y_ptr = nullptr;
+  plan->tmap_r_ptr = nullptr;
+  return DRNB200_OK;
+}
+
+// output-shaped NHWC tensor, box = one staged chunk (128 couts x ep_cw x ep_ch pixels), no swizzle
+static int encode_out_tmap(drnb200_conv_plan* plan, CUtensorMap* map, const void* ptr) {
+  const ConvParams& p = plan->p;
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return DRNB200_E_CUDA;
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.N};
+  cuuint64_t gstr[3] = {(cuuint64_t)p.Cout * 2, (cuuint64_t)p.OW * p.Cout * 2,
+                        (cuuint64_t)p.OH * p.OW * p.Cout * 2};
+  cuuint32_t box[4] = {128, (cuuint32_t)p.ep_cw, (cuuint32_t)p.ep_ch, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapDataType dt = plan->d.act_dtype == DRNB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                             : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(map, dt, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(out) failed with CUresult %d (Cout=%d OW=%d OH=%d N=%d box=%u,%u,%u)",
+              (int)r, p.Cout, p.OW, p.OH, p.N, box[0], box[1], box[2]);
+    return DRNB200_E_CUDA;
+  }
   return DRNB200_OK;
 }
 
@@ -419,16 +558,35 @@ int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st) {
     int rc = encode_tmap(plan, p.x);
     if (rc) return rc;
   }
+  if (plan->tc_mode == MODE_T) {
+    if (plan->tmap_y_ptr != p.y) {
+      int rc = encode_out_tmap(plan, &plan->tmap_y, p.y);
+      if (rc) return rc;
+      plan->tmap_y_ptr = p.y;
+    }
+    if (p.has_res && plan->tmap_r_ptr != p.residual) {
+      int rc = encode_out_tmap(plan, &plan->tmap_r, p.residual);
+      if (rc) return rc;
+      plan->tmap_r_ptr = p.residual;
+    }
+    if (!p.has_res && plan->tmap_r_ptr == nullptr) plan->tmap_r = plan->tmap_y;   // never dereferenced
+  } else if (plan->tmap_y_ptr == nullptr) {
+    plan->tmap_y = plan->tmap;                                                    // unused by these modes
+    plan->tmap_r = plan->tmap;
+    plan->tmap_y_ptr = p.x;
+  }
   if (p.total_tiles == 0) return DRNB200_OK;
   const dim3 grid(plan->grid), block(kTcThreads);
   const bool bf = plan->d.act_dtype == DRNB200_BF16;
-  if (plan->tc_mode == MODE_T) {
-    if (bf) conv_tc_kernel<MODE_T, DRNB200_BF16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, p);
-    else    conv_tc_kernel<MODE_T, DRNB200_F16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, p);
-  } else {
-    if (bf) conv_tc_kernel<MODE_P, DRNB200_BF16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, p);
-    else    conv_tc_kernel<MODE_P, DRNB200_F16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, p);
-  }
+#define DRN_LAUNCH(M)                                                                                   \
+  do {                                                                                                  \
+    if (bf) conv_tc_kernel<M, DRNB200_BF16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, p); \
+    else    conv_tc_kernel<M, DRNB200_F16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, p);  \
+  } while (0)
+  if (plan->tc_mode == MODE_T) DRN_LAUNCH(MODE_T);
+  else if (plan->tc_mode == MODE_TD) DRN_LAUNCH(MODE_TD);
+  else DRN_LAUNCH(MODE_P);
+#undef DRN_LAUNCH
   DRN_CUDA(cudaGetLastError());
   return DRNB200_OK;
 }

@@ -178,6 +178,8 @@ class Engine:
         self.ops = []          # ConvLayer list in execution order
         self.head_plans = {}
         self.head_version = None
+        self.stem_plans = {}
+        self.stem_impl = "tcgen05"   # or "direct": CUDA-core fp32 stem (no input rounding), cross-check
         self.launches_per_forward = 0
         self._build_graph()
 
@@ -285,6 +287,7 @@ class Engine:
                                ).contiguous()
             self.stem_w = conv.weight.detach().to(device, torch.float32).contiguous()
             self._stem_version = ver
+            self._drop_stem_plans()
         seg = self.m.seg
         hver = (seg.weight._version, seg.bias._version, self.act_dtype, str(device))
         if self.head_version != hver:
@@ -296,6 +299,23 @@ class Engine:
             self.seg_b = seg.bias.detach().to(device, torch.float32).contiguous()
             self.head_version = hver
         return rebuilt
+
+    def _drop_stem_plans(self):
+        lib = ffi.lib()
+        for p in self.stem_plans.values():
+            lib.drnb200_stem_plan_destroy(p)
+        self.stem_plans = {}
+
+    def _stem_plan(self, N, H, W):
+        k = (N, H, W, self.act_dtype)
+        p = self.stem_plans.get(k)
+        if p is None:
+            hdl = C.c_void_p()
+            ffi.check(ffi.lib().drnb200_stem_plan_create(
+                C.byref(hdl), ffi.ptr(self.stem_w), ffi.ptr(self.stem_scale), ffi.ptr(self.stem_shift),
+                N, H, W, self.stem[0].out_channels, self.act_dtype, ffi.stream_ptr()), "stem_plan_create")
+            p = self.stem_plans[k] = hdl
+        return p
 
     def _head_plan(self, N, h, w):
         k = (N, h, w)
@@ -381,9 +401,13 @@ class Engine:
         c0 = sconv.out_channels
         y = take(N * H * W * c0)
         with timed("stem"):
-            ffi.check(lib.drnb200_stem_forward(ffi.ptr(x), ffi.ptr(self.stem_w), ffi.ptr(self.stem_scale),
-                                               ffi.ptr(self.stem_shift), N, H, W, c0, adt, ffi.ptr(y), st),
-                      "stem_forward")
+            if self.stem_impl == "direct":
+                ffi.check(lib.drnb200_stem_forward(ffi.ptr(x), ffi.ptr(self.stem_w), ffi.ptr(self.stem_scale),
+                                                   ffi.ptr(self.stem_shift), N, H, W, c0, adt, ffi.ptr(y), st),
+                          "stem_forward")
+            else:
+                ffi.check(lib.drnb200_stem_plan_forward(self._stem_plan(N, H, W), ffi.ptr(x), ffi.ptr(y), st),
+                          "stem_plan_forward")
         launches += 1
         outs[-1] = y
         for i, op in enumerate(self.ops):
@@ -423,3 +447,4 @@ class Engine:
         for p in self.head_plans.values():
             lib.drnb200_head_plan_destroy(p)
         self.head_plans = {}
+        self._drop_stem_plans()

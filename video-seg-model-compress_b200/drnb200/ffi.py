@@ -41,6 +41,10 @@ SIGNATURES = {
     "drnb200_conv_plan_destroy": (None, [_P]),
     "drnb200_stem_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        _P, _P]),
+    "drnb200_stem_plan_create": (C.c_int, [C.POINTER(_P), _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, _P]),
+    "drnb200_stem_plan_forward": (C.c_int, [_P, _P, _P, _P]),
+    "drnb200_stem_plan_destroy": (None, [_P]),
     "drnb200_head_plan_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_int, _P, _P, _P]),
     "drnb200_head_forward": (C.c_int, [_P, _P, _P, _P, _P, _P]),
