@@ -228,7 +228,7 @@ static int run_conv(const ConvCase& c) {
 }
 
 // ------------------------------------------------------------------------------------ stem
-static int run_stem(int dt, int use_plan = 0, int N = 2, int H = 20, int W = 70) {
+static int run_stem(int dt, int use_plan = 0, int N = 2, int H = 20, int W = 72) {
   const int C0 = 16;
   std::vector<float> x((size_t)N * 3 * H * W), w(C0 * 147), sc(C0), sh(C0);
   for (auto& v : x) v = frand();

@@ -2,27 +2,34 @@
 //
 // The TMA path of conv_tc.cu issues one box per filter tap; with 16 input channels a tap is a 32-byte row
 // and the kernel becomes TMA-issue / L2-request bound (measured: 2.9 ms for DRN-D-22 layer1 at batch 8,
-// 17x its HBM floor).  Here the 128-pixel x K im2col tile is gathered with plain 16-byte loads (the 9x
-// tap re-use is served by L1), written straight into the UMMA SWIZZLE_32B K-major layout, and multiplied
-// by weights that stay resident in shared memory for the whole persistent CTA:
+// 17x its HBM floor).  Here ONE TMA box per tile brings the input halo (tile + filter apron, zero-filled
+// outside the image = the conv padding) into shared memory, the CTA's threads expand it into the
+// 128-pixel x K im2col tile directly in the UMMA SWIZZLE_32B K-major layout (smem -> smem, no global
+// re-reads), and the weights stay resident in shared memory for the whole persistent CTA:
 //   MODE 3x3 : x NHWC 16-bit with exactly 16 channels, K-block = one tap (drn.py:201-211 layer1/layer2)
 //   MODE stem: x NCHW float32 with 3 channels, 7x7, K = 147 padded to 160; the fp32 -> 16-bit conversion of
-//              the frame is fused into the gather (drn.py:132-137; callers pass fp32 NCHW, semantic_seg.py:440)
+//              the frame is fused into the expansion (drn.py:132-137; callers pass fp32 NCHW, semantic_seg.py:440)
 // GEMM orientation: M = 128 output pixels (TMEM lanes), N = Cout (16 or 32 columns), K-step = 16.
-// Roles (288 threads): warps 0-7 gather (256 threads: pixel m = tid & 127, chunk parity = tid >> 7),
-// warps 0-3 also run the epilogue of the previous tile, warp 8 allocates TMEM and issues the MMAs.
-// Two im2col buffers and two TMEM accumulators software-pipeline gather(i+1) | MMA(i) | epilogue(i-1).
+// Roles (448 threads): warps 0-7 expand (256 threads), warp 8 allocates TMEM and issues the MMAs,
+// warp 9 issues the halo TMA loads up to G_HRING tiles ahead, warps 10-13 run the epilogue.
+// A ring of halo buffers, two im2col buffers and two TMEM accumulators pipeline
+//   TMA(i+k) | expand(i+1) | MMA(i) | epilogue(i-1)   with every stage on its own warps.
 #include "conv_internal.cuh"
 #include <algorithm>
+#include <cudaTypedefs.h>
 #include <new>
 
 namespace drnb200 {
 
-constexpr int G_THREADS = 288;
+constexpr int G_THREADS = 448;          // 8 expand warps, MMA warp, TMA warp, 4 epilogue warps
 constexpr int G_MAX_KB = 10;            // 9 taps, or 160/16 stem K-blocks
 constexpr int G_KB_BYTES = 128 * 32;    // one K-block of the im2col tile: 128 pixels x 16 elements
 constexpr int G_ABUF_BYTES = G_MAX_KB * G_KB_BYTES;
 constexpr uint32_t G_TMEM_COLS = 64;    // 2 accumulators x 32 columns
+constexpr int G_TW = 32, G_TH = 4;      // output tile: 32 x 4 pixels
+constexpr int G_STEM_HW = 40, G_STEM_HH = G_TH + 6;         // stem halo: 3 planes x 10 rows x 40 floats
+constexpr int G_HALO_BYTES = 20480;     // >= 9*65*32 (3x3 stride 2), 6*34*32 (stride 1), 3*10*40*4 (stem)
+constexpr int G_HRING = 6;              // halo ring depth: TMA latency (~2 us) >> per-tile time (~0.3 us)
 
 struct GatherParams {
   const void* x;
@@ -34,31 +41,72 @@ struct GatherParams {
   int n_kb;
   int N, H, W, OH, OW, Cout, stride, relu;
   int stem;                  // 0: 3x3 over NHWC 16-channel input, 1: 7x7 over NCHW fp32 3-channel input
-  int TW, TH, tw_shift, tiles_x, tiles_y, total_tiles;
+  int tiles_x, tiles_y, total_tiles;
+  int halo_w, halo_h;        // 3x3: halo box in pixels
+  uint32_t halo_bytes;
   uint32_t idesc;
 };
 
 struct __align__(8) GSync {
-  uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2];
+  uint64_t h_full[G_HRING], h_empty[G_HRING], a_full[2], a_empty[2], t_full[2], t_empty[2];
   uint32_t tmem_base, pad;
 };
 
-// k -> (ci, ky-3, kx-3) of the 7x7 stem, k = ci*49 + ky*7 + kx (OIHW flattening); k >= 147 is padding
-__constant__ int c_stem_lut[160];
+struct GTile { int n, ox0, oy0; };
+__device__ __forceinline__ GTile g_decode(const GatherParams& p, int t) {
+  GTile c;
+  const int txi = t % p.tiles_x; t /= p.tiles_x;
+  const int tyi = t % p.tiles_y;
+  c.n = t / p.tiles_y;
+  c.ox0 = txi * G_TW; c.oy0 = tyi * G_TH;
+  return c;
+}
+
+// halo float offset of stem element k (k = ci*49 + ky*7 + kx); the halo origin is (ox0-4, oy0-3)
+__host__ __device__ constexpr int stem_halo_off(int k) {
+  return ((k / 49) * G_STEM_HH + (k % 49) / 7) * G_STEM_HW + (k % 7) + 1;
+}
+
+// chunks HALF, HALF+2, ... of one pixel's 160-element im2col row, offsets resolved at compile time
+template <int DT, int HALF>
+__device__ __forceinline__ void stem_expand(const float* hp, uint8_t* a, int m) {
+#pragma unroll
+  for (int cc = 0; cc < G_MAX_KB; ++cc) {
+    constexpr int dummy = 0; (void)dummy;
+    const int c = 2 * cc + HALF;
+    uint32_t w[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      const int k0 = c * 8 + e2 * 2, k1 = k0 + 1;
+      const float f0 = k0 < 147 ? hp[stem_halo_off(k0)] : 0.f;
+      const float f1 = k1 < 147 ? hp[stem_halo_off(k1)] : 0.f;
+      w[e2] = (uint32_t)Act<DT>::from_f32(f0) | ((uint32_t)Act<DT>::from_f32(f1) << 16);
+    }
+    *reinterpret_cast<uint4*>(a + (c >> 1) * G_KB_BYTES + swz_offset((uint32_t)m, (uint32_t)(c & 1), 32)) =
+        make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
 
 template <int DT>
-__global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const GatherParams p) {
+__global__ void __launch_bounds__(G_THREADS, 1)
+conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* abuf = smem;                                   // 2 x G_ABUF_BYTES
-  uint8_t* wsm = smem + 2 * G_ABUF_BYTES;                 // n_kb x Cout x 32 B
+  uint8_t* halo = smem + 2 * G_ABUF_BYTES;                // G_HRING x G_HALO_BYTES
+  uint8_t* wsm = halo + G_HRING * G_HALO_BYTES;           // n_kb x Cout x 32 B
   GSync* sync = reinterpret_cast<GSync*>(wsm + G_MAX_KB * 32 * 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int b = 0; b < G_HRING; ++b) {
+      mbar_init(&sync->h_full[b], 1);
+      mbar_init(&sync->h_empty[b], 8);    // one arrive per expanding warp
+    }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&sync->a_full[b], 256);
+      mbar_init(&sync->a_full[b], 8);
       mbar_init(&sync->a_empty[b], 1);
       mbar_init(&sync->t_full[b], 1);
       mbar_init(&sync->t_empty[b], 4);
@@ -69,8 +117,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const GatherP
     tmem_alloc(&sync->tmem_base, G_TMEM_COLS);
     tmem_relinquish();
   }
-  // resident weights: plain 16-byte copies (a few KB, once per CTA)
-  {
+  {  // resident weights: plain 16-byte copies (a few KB, once per CTA)
     const int n16 = p.n_kb * p.Cout * 2;
     const uint4* src = reinterpret_cast<const uint4*>(p.w_packed);
     uint4* dst = reinterpret_cast<uint4*>(wsm);
@@ -83,7 +130,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const GatherP
   const uint32_t tmem_base = sync->tmem_base;
   const int w_kb_bytes = p.Cout * 32;
 
-  if (warp == 8) {
+  if (warp == 9) {
+    // ================================================================= halo TMA producer
+    if (lane == 0) {
+      int i = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+        const int b = i % G_HRING;
+        const GTile c = g_decode(p, t);
+        mbar_wait(&sync->h_empty[b], ((uint32_t)(i / G_HRING) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&sync->h_full[b], p.halo_bytes);
+        if (p.stem)   // tensor {W, H, 3, N} fp32, box {40, 10, 3, 1}; x origin ox0-4 keeps the box 16-byte aligned
+          tma_load_4d(&tmap_x, &sync->h_full[b], halo + b * G_HALO_BYTES, c.ox0 - 4, c.oy0 - 3, 0, c.n);
+        else          // tensor {16, W, H, N} 16-bit, box {16, halo_w, halo_h, 1}
+          tma_load_4d(&tmap_x, &sync->h_full[b], halo + b * G_HALO_BYTES, 0, c.ox0 * p.stride - 1,
+                      c.oy0 * p.stride - 1, c.n);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
     // ================================================================= MMA issuer
     if (lane == 0) {
       int i = 0;
@@ -102,26 +166,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const GatherP
       }
     }
     __syncwarp();
-  } else {
-    // ================================================================= gather (+ epilogue on warps 0-3)
-    const int m = tid & 127, half = tid >> 7;
-    const uint16_t* x16 = reinterpret_cast<const uint16_t*>(p.x);
-    const float* x32 = reinterpret_cast<const float*>(p.x);
+  } else if (warp >= 10) {
+    // ================================================================= epilogue (warps 10..13)
     uint16_t* y16 = reinterpret_cast<uint16_t*>(p.y);
-
-    auto epilogue = [&](int i, int t) {
-      if (warp >= 4) return;
+    const int q = warp & 3;                                // TMEM lane quarter of this warp
+    const int m = q * 32 + lane;                           // TMEM lane = pixel of the tile
+    int i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
       const int b = i & 1;
       mbar_wait(&sync->t_full[b], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
-      int pt = t;
-      const int txi = pt % p.tiles_x; pt /= p.tiles_x;
-      const int tyi = pt % p.tiles_y;
-      const int n = pt / p.tiles_y;
-      const int ox = txi * p.TW + (m & (p.TW - 1)), oy = tyi * p.TH + (m >> p.tw_shift);
+      const GTile c = g_decode(p, t);
+      const int ox = c.ox0 + (m & (G_TW - 1)), oy = c.oy0 + (m / G_TW);
       const bool valid = ox < p.OW && oy < p.OH;
-      const uint32_t t_addr = tmem_base + b * 32u + ((uint32_t)(warp * 32) << 16);
-      uint16_t* yp = y16 + (((size_t)n * p.OH + oy) * p.OW + ox) * p.Cout;
+      const uint32_t t_addr = tmem_base + b * 32u + ((uint32_t)(q * 32) << 16);
+      uint16_t* yp = y16 + (((size_t)c.n * p.OH + oy) * p.OW + ox) * p.Cout;
       for (int cb = 0; cb < p.Cout; cb += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + (uint32_t)cb, v);
@@ -131,10 +190,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const GatherP
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             float a = fmaf(__uint_as_float(v[2 * e]), __ldg(p.scale + cb + 2 * e), __ldg(p.shift + cb + 2 * e));
-            float c = fmaf(__uint_as_float(v[2 * e + 1]), __ldg(p.scale + cb + 2 * e + 1),
+            float d = fmaf(__uint_as_float(v[2 * e + 1]), __ldg(p.scale + cb + 2 * e + 1),
                            __ldg(p.shift + cb + 2 * e + 1));
-            if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-            w[e] = (uint32_t)Act<DT>::from_f32(a) | ((uint32_t)Act<DT>::from_f32(c) << 16);
+            if (p.relu) { a = fmaxf(a, 0.f); d = fmaxf(d, 0.f); }
+            w[e] = (uint32_t)Act<DT>::from_f32(a) | ((uint32_t)Act<DT>::from_f32(d) << 16);
           }
           uint4* o = reinterpret_cast<uint4*>(yp + cb);
           o[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -144,66 +203,54 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const GatherP
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sync->t_empty[b]);
-    };
-
-    int i = 0, t_prev = -1;
+    }
+  } else {
+    // ================================================================= expand
+    // 3x3: byte offset of every live tap inside the halo (constant for the whole kernel)
+    int tap_off[9];
+#pragma unroll
+    for (int kb = 0; kb < 9; ++kb) {
+      tap_off[kb] = 0;
+      if (!p.stem && kb < p.n_kb) {
+        const int tap = __ldg(p.kblk + kb);
+        tap_off[kb] = ((tap / 3) * p.halo_w + (tap % 3)) * 32;
+      }
+    }
+    int i = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-      const int b = i & 1;
-      mbar_wait(&sync->a_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);
-      int pt = t;
-      const int txi = pt % p.tiles_x; pt /= p.tiles_x;
-      const int tyi = pt % p.tiles_y;
-      const int n = pt / p.tiles_y;
-      const int ox = txi * p.TW + (m & (p.TW - 1)), oy = tyi * p.TH + (m >> p.tw_shift);
+      const int b = i & 1, hb = i % G_HRING;
+      const uint32_t par = (uint32_t)(i >> 1) & 1u;
+      mbar_wait(&sync->h_full[hb], (uint32_t)(i / G_HRING) & 1u);   // halo of this tile has landed
+      mbar_wait(&sync->a_empty[b], par ^ 1u);     // the MMAs that read this im2col buffer have retired
+      const uint8_t* h = halo + hb * G_HALO_BYTES;
       uint8_t* a = abuf + b * G_ABUF_BYTES;
       if (!p.stem) {
-        // K-block = tap: 16 channels = two 16-byte chunks; this thread copies chunk `half`
-        const int iy0 = oy * p.stride - 1, ix0 = ox * p.stride - 1;
-        uint4 vals[9];
-#pragma unroll
-        for (int kb = 0; kb < 9; ++kb) {
-          vals[kb] = make_uint4(0u, 0u, 0u, 0u);
-          if (kb < p.n_kb) {
-            const int tap = __ldg(p.kblk + kb);
-            const int iy = iy0 + tap / 3, ix = ix0 + tap % 3;
-            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-              vals[kb] = __ldg(reinterpret_cast<const uint4*>(
-                                   x16 + (((size_t)n * p.H + iy) * p.W + ix) * 16) + half);
-          }
-        }
+        // thread = (pixel m, 16-byte half of its 16 channels); a K-block is one filter tap
+        const int m = tid >> 1, half = tid & 1;
+        const int hx = (m & (G_TW - 1)) * p.stride, hy = (m / G_TW) * p.stride;
+        const uint8_t* src0 = h + ((size_t)hy * p.halo_w + hx) * 32 + half * 16;
+        uint8_t* dst0 = a + swz_offset((uint32_t)m, (uint32_t)half, 32);
+        uint4 v[9];
 #pragma unroll
         for (int kb = 0; kb < 9; ++kb)
-          if (kb < p.n_kb)
-            *reinterpret_cast<uint4*>(a + kb * G_KB_BYTES + swz_offset((uint32_t)m, (uint32_t)half, 32)) =
-                vals[kb];
+          if (kb < p.n_kb) v[kb] = *reinterpret_cast<const uint4*>(src0 + tap_off[kb]);
+#pragma unroll
+        for (int kb = 0; kb < 9; ++kb)
+          if (kb < p.n_kb) *reinterpret_cast<uint4*>(dst0 + kb * G_KB_BYTES) = v[kb];
       } else {
-        // stem: chunk c holds k = 8c .. 8c+7 of this pixel; this thread builds chunks half, half+2, ...
-        const float* xn = x32 + (size_t)n * 3 * p.H * p.W;
-        for (int c = half; c < 2 * G_MAX_KB; c += 2) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e2 = 0; e2 < 4; ++e2) {
-            float f[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int lut = c_stem_lut[c * 8 + e2 * 2 + u];
-              const int ci = lut & 3, iy = oy + ((lut >> 2) & 15) - 3, ix = ox + ((lut >> 6) & 15) - 3;
-              f[u] = 0.f;
-              if (ci < 3 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-                f[u] = __ldg(xn + ((size_t)ci * p.H + iy) * p.W + ix);
-            }
-            w[e2] = (uint32_t)Act<DT>::from_f32(f[0]) | ((uint32_t)Act<DT>::from_f32(f[1]) << 16);
-          }
-          *reinterpret_cast<uint4*>(a + (c >> 1) * G_KB_BYTES + swz_offset((uint32_t)m, (uint32_t)(c & 1), 32)) =
-              make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        // stem: thread = (pixel m, chunk parity); chunk c holds k = 8c .. 8c+7 (k = ci*49 + ky*7 + kx)
+        const int m = tid & 127;
+        const float* hp = reinterpret_cast<const float*>(h) + (m / G_TW) * G_STEM_HW + (m & (G_TW - 1));
+        if (tid < 128) stem_expand<DT, 0>(hp, a, m);
+        else stem_expand<DT, 1>(hp, a, m);
       }
       fence_proxy_async_smem();              // im2col tile -> visible to the tensor core (async proxy)
-      mbar_arrive(&sync->a_full[b]);
-      if (t_prev >= 0) epilogue(i - 1, t_prev);
-      t_prev = t;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sync->a_full[b]);
+        mbar_arrive(&sync->h_empty[hb]);     // halo buffer may be refilled
+      }
     }
-    if (t_prev >= 0) epilogue(i - 1, t_prev);
   }
 
   tc_fence_before();
@@ -214,25 +261,67 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv_gather_kernel(const GatherP
   }
 }
 
-static int ilog2i(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+  return fn;
+}
 
-static int gather_launch(GatherParams& p, int act_dtype, cudaStream_t st) {
-  static bool lut_done = false;
-  if (!lut_done) {
-    int lut[160];
-    for (int k = 0; k < 160; ++k) {
-      if (k < 147) { const int ci = k / 49, ky = (k % 49) / 7, kx = k % 7; lut[k] = ci | (ky << 2) | (kx << 6); }
-      else lut[k] = 3;   // ci == 3: padding element
-    }
-    DRN_CUDA(cudaMemcpyToSymbol(c_stem_lut, lut, sizeof(lut)));
-    lut_done = true;
-  }
-  p.TW = 32; p.TH = 4; p.tw_shift = ilog2i(p.TW);
-  p.tiles_x = (p.OW + p.TW - 1) / p.TW;
-  p.tiles_y = (p.OH + p.TH - 1) / p.TH;
+// cached halo tensor map per (pointer, geometry)
+struct GMapCache {
+  const void* ptr = nullptr;
+  int N = 0, H = 0, W = 0, stride = 0, stem = -1, dt = -1;
+  CUtensorMap map;
+};
+
+static int gather_launch(GatherParams& p, int act_dtype, GMapCache& cache, cudaStream_t st) {
+  p.tiles_x = (p.OW + G_TW - 1) / G_TW;
+  p.tiles_y = (p.OH + G_TH - 1) / G_TH;
   p.total_tiles = p.N * p.tiles_x * p.tiles_y;
   p.idesc = umma_idesc_f16(128, p.Cout, act_dtype);
-  const size_t smem = 1024 + 2 * G_ABUF_BYTES + G_MAX_KB * 32 * 32 + sizeof(GSync);
+  if (p.stem) {
+    p.halo_w = G_STEM_HW; p.halo_h = G_STEM_HH;
+    p.halo_bytes = 3 * G_STEM_HH * G_STEM_HW * 4;
+  } else {
+    p.halo_w = (G_TW - 1) * p.stride + 3; p.halo_h = (G_TH - 1) * p.stride + 3;
+    p.halo_bytes = (uint32_t)p.halo_w * p.halo_h * 32;
+  }
+  if (cache.ptr != p.x || cache.N != p.N || cache.H != p.H || cache.W != p.W || cache.stride != p.stride ||
+      cache.stem != p.stem || cache.dt != act_dtype) {
+    auto fn = g_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return DRNB200_E_CUDA; }
+    CUresult r;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (p.stem) {
+      cuuint64_t gdim[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, 3, (cuuint64_t)p.N};
+      cuuint64_t gstr[3] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.W * p.H * 4, (cuuint64_t)p.W * p.H * 12};
+      cuuint32_t box[4] = {(cuuint32_t)G_STEM_HW, (cuuint32_t)G_STEM_HH, 3, 1};
+      r = fn(&cache.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p.x), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t gdim[4] = {16, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+      cuuint64_t gstr[3] = {32, (cuuint64_t)p.W * 32, (cuuint64_t)p.W * p.H * 32};
+      cuuint32_t box[4] = {16, (cuuint32_t)p.halo_w, (cuuint32_t)p.halo_h, 1};
+      r = fn(&cache.map, act_dtype == DRNB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+             4, const_cast<void*>(p.x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(halo) failed with CUresult %d (stem=%d W=%d H=%d N=%d)", (int)r, p.stem,
+                p.W, p.H, p.N);
+      return DRNB200_E_CUDA;
+    }
+    cache.ptr = p.x; cache.N = p.N; cache.H = p.H; cache.W = p.W; cache.stride = p.stride; cache.stem = p.stem;
+    cache.dt = act_dtype;
+  }
+  const size_t smem = 1024 + 2 * G_ABUF_BYTES + G_HRING * G_HALO_BYTES + G_MAX_KB * 32 * 32 + sizeof(GSync);
   static bool attr_done[2] = {false, false};
   if (!attr_done[act_dtype]) {
     if (act_dtype == DRNB200_BF16)
@@ -248,8 +337,8 @@ static int gather_launch(GatherParams& p, int act_dtype, cudaStream_t st) {
   DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = std::min(p.total_tiles, sms);
   if (grid == 0) return DRNB200_OK;
-  if (act_dtype == DRNB200_BF16) conv_gather_kernel<DRNB200_BF16><<<grid, G_THREADS, smem, st>>>(p);
-  else conv_gather_kernel<DRNB200_F16><<<grid, G_THREADS, smem, st>>>(p);
+  if (act_dtype == DRNB200_BF16) conv_gather_kernel<DRNB200_BF16><<<grid, G_THREADS, smem, st>>>(cache.map, p);
+  else conv_gather_kernel<DRNB200_F16><<<grid, G_THREADS, smem, st>>>(cache.map, p);
   DRN_CUDA(cudaGetLastError());
   return DRNB200_OK;
 }
@@ -270,7 +359,10 @@ int conv_gather_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   if (p.n_kb == 0) {        // everything pruned: y = act(shift); the direct kernel handles that corner
     return conv_direct_launch(plan, st);
   }
-  return gather_launch(p, plan->d.act_dtype, st);
+  static_assert(sizeof(GMapCache) <= sizeof(plan->gather_cache), "gather cache storage too small");
+  GMapCache* cache = reinterpret_cast<GMapCache*>(plan->gather_cache);
+  if (!plan->gather_cache_init) { new (cache) GMapCache(); plan->gather_cache_init = true; }
+  return gather_launch(p, plan->d.act_dtype, *cache, st);
 }
 
 // ----------------------------------------------------------------------------------------------- stem plan
@@ -290,6 +382,7 @@ __global__ void stem_pad_kernel(const float* __restrict__ w, float* __restrict__
 using namespace drnb200;
 
 struct drnb200_stem_plan {
+  drnb200::GMapCache cache;
   int N, H, W, act_dtype;
   float *d_wpad, *d_scale, *d_shift;
   int32_t *d_row_ptr, *d_kblk;
@@ -312,7 +405,6 @@ extern "C" int drnb200_stem_plan_create(drnb200_stem_plan** out, const float* w_
   DRN_REQUIRE(act_dtype == DRNB200_BF16 || act_dtype == DRNB200_F16, "stem_plan_create: bad act_dtype");
   drnb200_stem_plan* p = new (std::nothrow) drnb200_stem_plan();
   if (!p) { set_error("stem_plan_create: out of host memory"); return DRNB200_E_NOMEM; }
-  *p = drnb200_stem_plan{};
   p->N = N; p->H = H; p->W = W; p->act_dtype = act_dtype;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
@@ -346,5 +438,5 @@ extern "C" int drnb200_stem_plan_forward(drnb200_stem_plan* plan, const float* x
   p.kblk = plan->d_kblk; p.scale = plan->d_scale; p.shift = plan->d_shift; p.n_kb = G_MAX_KB;
   p.N = plan->N; p.H = plan->H; p.W = plan->W; p.OH = plan->H; p.OW = plan->W; p.Cout = 16;
   p.stride = 1; p.relu = 1; p.stem = 1;
-  return gather_launch(p, plan->act_dtype, (cudaStream_t)stream);
+  return gather_launch(p, plan->act_dtype, plan->cache, (cudaStream_t)stream);
 }

@@ -48,6 +48,8 @@ struct drnb200_conv_plan {
   const void* tmap_y_ptr;
   const void* tmap_r_ptr;
   std::vector<int32_t> h_row_ptr;
+  alignas(64) unsigned char gather_cache[256];   // GMapCache of conv_gather.cu (halo tensor map)
+  bool gather_cache_init = false;
 };
 
 namespace drnb200 {
