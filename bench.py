@@ -217,25 +217,41 @@ def main():
         launches = (eng.launches_per_forward + 1) * args.steps
         miou = meter.miou()
 
-        # ---- e2e: host frames -> H2D -> predict -> D2H labels, through the public API
+        # ---- e2e: host frames -> H2D -> predict -> D2H labels, through the public API.
+        # A user-side double buffer: frame batch i+1 is copied in on a side stream while batch i is
+        # segmented; every step still moves its own input from pinned host memory and its labels back.
         hx = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
         hx.copy_(x.cpu())
-        hl = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
-        xd = torch.empty_like(x)
+        hl = [torch.empty((B, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        xd = [torch.empty_like(x) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_step():
-            xd.copy_(hx, non_blocking=True)
-            labels = model.predict(xd)
-            hl.copy_(labels, non_blocking=True)
+        def e2e_run(n_steps):
+            for s_ in range(n_steps + 1):
+                if s_ < n_steps:                      # stage batch s_ on the copy stream
+                    b = s_ & 1
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(consumed[b])
+                        xd[b].copy_(hx, non_blocking=True)
+                        ready[b].record(copy_stream)
+                if s_ >= 1:                           # segment batch s_-1 on the main stream
+                    b = (s_ - 1) & 1
+                    main_stream.wait_event(ready[b])
+                    labels = model.predict(xd[b])
+                    consumed[b].record(main_stream)
+                    hl[b].copy_(labels, non_blocking=True)
 
-        for _ in range(2):
-            e2e_step()
+        for b in range(2):
+            consumed[b].record(main_stream)
+        e2e_run(2)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         f0.record()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_run(args.steps)
         f1.record()
         barrier()
         e2e_wall = time.perf_counter() - t0
