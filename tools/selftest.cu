@@ -377,6 +377,8 @@ static const ConvCase kCases[] = {
     {"tcT_big_sparse",     2, 64,128, 512,512, 3, 1, 4, 1, 1, 0, 0, 128, 64, 2, 0.25f,0, 0, 1},
     {"tcT_big_dense",      2, 64,128, 256,512, 3, 1, 2, 1, 0, 0, 0, 128, 64, 2, 1.0f, 0, 0, 1},
     {"tcP_16_16",          1, 16, 32, 16,  16, 3, 1, 1, 1, 0, 0, 0,  16, 16, 2, 1.0f, 0, 0, 0},
+    {"tcH_d2",             1, 20, 24, 64,  64, 3, 1, 2, 1, 0, 0, 0,  64, 64, 2, 1.0f, 0, 0, 0},
+    {"tcH_32_d4",          2, 17, 19, 32,  32, 3, 1, 4, 1, 1, 1, 0,  32, 32, 2, 1.0f, 0, 0, 0},
     {"tcG_pertap",         1, 16, 32, 16,  16, 3, 1, 1, 1, 0, 0, 0,  16, 16, 2, 0.6f, 1, 0, 0},
     {"tcG_f16_odd",        2, 19, 45, 16,  32, 3, 2, 1, 1, 0, 1, 0,  32, 16, 2, 1.0f, 0, 0, 0},
     {"tcP_16_32_s2",       2, 18, 34, 16,  32, 3, 2, 1, 1, 0, 0, 0,  32, 16, 2, 1.0f, 0, 0, 0},

@@ -11,7 +11,8 @@
 //              the frame is fused into the expansion (drn.py:132-137; callers pass fp32 NCHW, semantic_seg.py:440)
 // GEMM orientation: M = 128 output pixels (TMEM lanes), N = Cout (16 or 32 columns), K-step = 16.
 // Roles (448 threads): warps 0-7 expand (256 threads), warp 8 allocates TMEM and issues the MMAs,
-// warp 9 issues the halo TMA loads up to G_HRING tiles ahead, warps 10-13 run the epilogue.
+// warp 9 issues the halo TMA loads up to G_HRING tiles ahead, warps 10-17 run the epilogue (two groups
+// of four warps on alternate tiles).
 // A ring of halo buffers, two im2col buffers and two TMEM accumulators pipeline
 //   TMA(i+k) | expand(i+1) | MMA(i) | epilogue(i-1)   with every stage on its own warps.
 #include "conv_internal.cuh"
@@ -21,15 +22,15 @@
 
 namespace drnb200 {
 
-constexpr int G_THREADS = 448;          // 8 expand warps, MMA warp, TMA warp, 4 epilogue warps
+constexpr int G_THREADS = 576;          // 8 expand warps, MMA warp, TMA warp, 2 x 4 epilogue warps
 constexpr int G_MAX_KB = 10;            // 9 taps, or 160/16 stem K-blocks
 constexpr int G_KB_BYTES = 128 * 32;    // one K-block of the im2col tile: 128 pixels x 16 elements
-constexpr int G_ABUF_BYTES = G_MAX_KB * G_KB_BYTES;
-constexpr uint32_t G_TMEM_COLS = 64;    // 2 accumulators x 32 columns
-constexpr int G_TW = 32, G_TH = 4;      // output tile: 32 x 4 pixels
-constexpr int G_STEM_HW = 40, G_STEM_HH = G_TH + 6;         // stem halo: 3 planes x 10 rows x 40 floats
-constexpr int G_HALO_BYTES = 20480;     // >= 9*65*32 (3x3 stride 2), 6*34*32 (stride 1), 3*10*40*4 (stem)
-constexpr int G_HRING = 6;              // halo ring depth: TMA latency (~2 us) >> per-tile time (~0.3 us)
+constexpr int G_MAX_ABUF = 4;            // im2col buffers: expand(i+k) | MMA(i) — two were latency-bound (measured)
+constexpr int G_ACC = 4;                // TMEM accumulator stages (MMA -> epilogue round trip >> tile time)
+constexpr uint32_t G_TMEM_COLS = 128;   // 4 accumulators x 32 columns
+constexpr int G_STEM_TW = 32, G_STEM_TH = 4;                // stem output tile: 32 x 4 pixels
+constexpr int G_STEM_HW = 40, G_STEM_HH = G_STEM_TH + 6;    // stem halo: 3 planes x 10 rows x 40 floats
+constexpr int G_HRING = 6;              // max halo ring depth: TMA latency (~2 us) >> per-tile time (~0.3 us)
 
 struct GatherParams {
   const void* x;
@@ -41,14 +42,19 @@ struct GatherParams {
   int n_kb;
   int N, H, W, OH, OW, Cout, stride, relu;
   int stem;                  // 0: 3x3 over NHWC 16-channel input, 1: 7x7 over NCHW fp32 3-channel input
+  int TW, TH, tw_shift;      // output tile (32x4; 16x8 for stride 2 so that the halo row fits one TMA box row)
   int tiles_x, tiles_y, total_tiles;
   int halo_w, halo_h;        // 3x3: halo box in pixels
-  uint32_t halo_bytes;
+  uint32_t halo_bytes;       // TMA transaction bytes of one halo box
+  uint32_t halo_stride;      // halo buffer pitch in shared memory (halo_bytes rounded up to 1 KB)
+  uint32_t abuf_bytes;       // one im2col buffer: n_kb x 4 KB
+  int n_abuf, ring;          // buffers that fit in shared memory
   uint32_t idesc;
 };
 
 struct __align__(8) GSync {
-  uint64_t h_full[G_HRING], h_empty[G_HRING], a_full[2], a_empty[2], t_full[2], t_empty[2];
+  uint64_t h_full[G_HRING], h_empty[G_HRING], a_full[G_MAX_ABUF], a_empty[G_MAX_ABUF],
+      t_full[G_ACC], t_empty[G_ACC];
   uint32_t tmem_base, pad;
 };
 
@@ -58,7 +64,7 @@ __device__ __forceinline__ GTile g_decode(const GatherParams& p, int t) {
   const int txi = t % p.tiles_x; t /= p.tiles_x;
   const int tyi = t % p.tiles_y;
   c.n = t / p.tiles_y;
-  c.ox0 = txi * G_TW; c.oy0 = tyi * G_TH;
+  c.ox0 = txi * p.TW; c.oy0 = tyi * p.TH;
   return c;
 }
 
@@ -93,9 +99,9 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* abuf = smem;                                   // 2 x G_ABUF_BYTES
-  uint8_t* halo = smem + 2 * G_ABUF_BYTES;                // G_HRING x G_HALO_BYTES
-  uint8_t* wsm = halo + G_HRING * G_HALO_BYTES;           // n_kb x Cout x 32 B
+  uint8_t* abuf = smem;                                   // n_abuf x abuf_bytes
+  uint8_t* halo = smem + (size_t)p.n_abuf * p.abuf_bytes; // ring x halo_stride
+  uint8_t* wsm = halo + (size_t)p.ring * p.halo_stride;   // n_kb x Cout x 32 B
   GSync* sync = reinterpret_cast<GSync*>(wsm + G_MAX_KB * 32 * 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -105,9 +111,11 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
       mbar_init(&sync->h_full[b], 1);
       mbar_init(&sync->h_empty[b], 8);    // one arrive per expanding warp
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < G_MAX_ABUF; ++b) {
       mbar_init(&sync->a_full[b], 8);
       mbar_init(&sync->a_empty[b], 1);
+    }
+    for (int b = 0; b < G_ACC; ++b) {
       mbar_init(&sync->t_full[b], 1);
       mbar_init(&sync->t_empty[b], 4);
     }
@@ -135,34 +143,41 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
     if (lane == 0) {
       int i = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-        const int b = i % G_HRING;
+        const int b = i % p.ring;
         const GTile c = g_decode(p, t);
-        mbar_wait(&sync->h_empty[b], ((uint32_t)(i / G_HRING) & 1u) ^ 1u);
+        mbar_wait(&sync->h_empty[b], ((uint32_t)(i / p.ring) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&sync->h_full[b], p.halo_bytes);
         if (p.stem)   // tensor {W, H, 3, N} fp32, box {40, 10, 3, 1}; x origin ox0-4 keeps the box 16-byte aligned
-          tma_load_4d(&tmap_x, &sync->h_full[b], halo + b * G_HALO_BYTES, c.ox0 - 4, c.oy0 - 3, 0, c.n);
-        else          // tensor {16, W, H, N} 16-bit, box {16, halo_w, halo_h, 1}
-          tma_load_4d(&tmap_x, &sync->h_full[b], halo + b * G_HALO_BYTES, 0, c.ox0 * p.stride - 1,
-                      c.oy0 * p.stride - 1, c.n);
+          tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_stride, c.ox0 - 4, c.oy0 - 3, 0, c.n);
+        else          // tensor {W*4, H, N, 1} of 8-byte elements (a pixel = 16 ch x 2 B = 4 elements), box
+                      // {halo_w*4, halo_h, 1, 1}: one box row per halo row.  (With a {16ch, px, rows} box every
+                      // pixel is its own 32-byte TMA row and the load is row-rate bound: ~5 cycles per row.)
+          tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_stride, (c.ox0 * p.stride - 1) * 4,
+                      c.oy0 * p.stride - 1, c.n, 0);
       }
     }
     __syncwarp();
   } else if (warp == 8) {
     // ================================================================= MMA issuer
     if (lane == 0) {
+      // loop-invariant descriptor parts hoisted: the single issuing thread is the critical path here
+      const uint64_t d_hi = umma_smem_desc(0u, 32);
+      const uint32_t w16 = smem_u32(wsm) >> 4, wk16 = (uint32_t)w_kb_bytes >> 4;
+      const int n_kb = p.n_kb;
       int i = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-        const int b = i & 1;
-        const uint32_t par = (uint32_t)(i >> 1) & 1u;
-        mbar_wait(&sync->a_full[b], par);
-        mbar_wait(&sync->t_empty[b], par ^ 1u);
+        const int b = i % p.n_abuf, ta = i % G_ACC;
+        mbar_wait(&sync->a_full[b], (uint32_t)(i / p.n_abuf) & 1u);
+        mbar_wait(&sync->t_empty[ta], ((uint32_t)(i / G_ACC) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(abuf + b * G_ABUF_BYTES), w0 = smem_u32(wsm);
-        for (int kb = 0; kb < p.n_kb; ++kb)
-          umma_f16(tmem_base + b * 32u, umma_smem_desc(a0 + kb * G_KB_BYTES, 32),
-                   umma_smem_desc(w0 + kb * w_kb_bytes, 32), p.idesc, kb > 0 ? 1u : 0u);
+        const uint32_t a16 = smem_u32(abuf + (size_t)b * p.abuf_bytes) >> 4;
+#pragma unroll
+        for (int kb = 0; kb < G_MAX_KB; ++kb)
+          if (kb < n_kb)
+            umma_f16(tmem_base + ta * 32u, d_hi | (uint64_t)(a16 + kb * (G_KB_BYTES >> 4)),
+                     d_hi | (uint64_t)(w16 + kb * wk16), p.idesc, kb > 0 ? 1u : 0u);
         umma_commit(&sync->a_empty[b]);
-        umma_commit(&sync->t_full[b]);
+        umma_commit(&sync->t_full[ta]);
       }
     }
     __syncwarp();
@@ -170,14 +185,14 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
     // ================================================================= epilogue (warps 10..13)
     uint16_t* y16 = reinterpret_cast<uint16_t*>(p.y);
     const int q = warp & 3;                                // TMEM lane quarter of this warp
+    const int grp = (warp - 10) >> 2;                      // epilogue group 0/1 takes alternate tiles
     const int m = q * 32 + lane;                           // TMEM lane = pixel of the tile
-    int i = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-      const int b = i & 1;
-      mbar_wait(&sync->t_full[b], (uint32_t)(i >> 1) & 1u);
+    for (int i = grp, t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += 2 * gridDim.x, i += 2) {
+      const int b = i % G_ACC;
+      mbar_wait(&sync->t_full[b], (uint32_t)(i / G_ACC) & 1u);
       tc_fence_after();
       const GTile c = g_decode(p, t);
-      const int ox = c.ox0 + (m & (G_TW - 1)), oy = c.oy0 + (m / G_TW);
+      const int ox = c.ox0 + (m & (p.TW - 1)), oy = c.oy0 + (m >> p.tw_shift);
       const bool valid = ox < p.OW && oy < p.OH;
       const uint32_t t_addr = tmem_base + b * 32u + ((uint32_t)(q * 32) << 16);
       uint16_t* yp = y16 + (((size_t)c.n * p.OH + oy) * p.OW + ox) * p.Cout;
@@ -218,16 +233,15 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
     }
     int i = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-      const int b = i & 1, hb = i % G_HRING;
-      const uint32_t par = (uint32_t)(i >> 1) & 1u;
-      mbar_wait(&sync->h_full[hb], (uint32_t)(i / G_HRING) & 1u);   // halo of this tile has landed
-      mbar_wait(&sync->a_empty[b], par ^ 1u);     // the MMAs that read this im2col buffer have retired
-      const uint8_t* h = halo + hb * G_HALO_BYTES;
-      uint8_t* a = abuf + b * G_ABUF_BYTES;
+      const int b = i % p.n_abuf, hb = i % p.ring;
+      mbar_wait(&sync->h_full[hb], (uint32_t)(i / p.ring) & 1u);    // halo of this tile has landed
+      mbar_wait(&sync->a_empty[b], ((uint32_t)(i / p.n_abuf) & 1u) ^ 1u);   // MMAs that read this buffer retired
+      const uint8_t* h = halo + (size_t)hb * p.halo_stride;
+      uint8_t* a = abuf + (size_t)b * p.abuf_bytes;
       if (!p.stem) {
         // thread = (pixel m, 16-byte half of its 16 channels); a K-block is one filter tap
         const int m = tid >> 1, half = tid & 1;
-        const int hx = (m & (G_TW - 1)) * p.stride, hy = (m / G_TW) * p.stride;
+        const int hx = (m & (p.TW - 1)) * p.stride, hy = (m >> p.tw_shift) * p.stride;
         const uint8_t* src0 = h + ((size_t)hy * p.halo_w + hx) * 32 + half * 16;
         uint8_t* dst0 = a + swz_offset((uint32_t)m, (uint32_t)half, 32);
         uint4 v[9];
@@ -240,7 +254,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
       } else {
         // stem: thread = (pixel m, chunk parity); chunk c holds k = 8c .. 8c+7 (k = ci*49 + ky*7 + kx)
         const int m = tid & 127;
-        const float* hp = reinterpret_cast<const float*>(h) + (m / G_TW) * G_STEM_HW + (m & (G_TW - 1));
+        const float* hp = reinterpret_cast<const float*>(h) + (m / G_STEM_TW) * G_STEM_HW + (m & (G_STEM_TW - 1));
         if (tid < 128) stem_expand<DT, 0>(hp, a, m);
         else stem_expand<DT, 1>(hp, a, m);
       }
@@ -281,15 +295,17 @@ struct GMapCache {
 };
 
 static int gather_launch(GatherParams& p, int act_dtype, GMapCache& cache, cudaStream_t st) {
-  p.tiles_x = (p.OW + G_TW - 1) / G_TW;
-  p.tiles_y = (p.OH + G_TH - 1) / G_TH;
+  if (p.stem || p.stride == 1) { p.TW = 32; p.TH = 4; p.tw_shift = 5; }
+  else { p.TW = 16; p.TH = 8; p.tw_shift = 4; }
+  p.tiles_x = (p.OW + p.TW - 1) / p.TW;
+  p.tiles_y = (p.OH + p.TH - 1) / p.TH;
   p.total_tiles = p.N * p.tiles_x * p.tiles_y;
   p.idesc = umma_idesc_f16(128, p.Cout, act_dtype);
   if (p.stem) {
     p.halo_w = G_STEM_HW; p.halo_h = G_STEM_HH;
     p.halo_bytes = 3 * G_STEM_HH * G_STEM_HW * 4;
   } else {
-    p.halo_w = (G_TW - 1) * p.stride + 3; p.halo_h = (G_TH - 1) * p.stride + 3;
+    p.halo_w = (p.TW - 1) * p.stride + 3; p.halo_h = (p.TH - 1) * p.stride + 3;
     p.halo_bytes = (uint32_t)p.halo_w * p.halo_h * 32;
   }
   if (cache.ptr != p.x || cache.N != p.N || cache.H != p.H || cache.W != p.W || cache.stride != p.stride ||
@@ -306,12 +322,12 @@ static int gather_launch(GatherParams& p, int act_dtype, GMapCache& cache, cudaS
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
-      cuuint64_t gdim[4] = {16, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
-      cuuint64_t gstr[3] = {32, (cuuint64_t)p.W * 32, (cuuint64_t)p.W * p.H * 32};
-      cuuint32_t box[4] = {16, (cuuint32_t)p.halo_w, (cuuint32_t)p.halo_h, 1};
-      r = fn(&cache.map, act_dtype == DRNB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-             4, const_cast<void*>(p.x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      cuuint64_t gdim[4] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H, (cuuint64_t)p.N, 1};
+      cuuint64_t gstr[3] = {(cuuint64_t)p.W * 32, (cuuint64_t)p.W * p.H * 32, (cuuint64_t)p.W * p.H * 32 * p.N};
+      cuuint32_t box[4] = {(cuuint32_t)p.halo_w * 4, (cuuint32_t)p.halo_h, 1, 1};
+      r = fn(&cache.map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(p.x), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(halo) failed with CUresult %d (stem=%d W=%d H=%d N=%d)", (int)r, p.stem,
@@ -321,7 +337,15 @@ static int gather_launch(GatherParams& p, int act_dtype, GMapCache& cache, cudaS
     cache.ptr = p.x; cache.N = p.N; cache.H = p.H; cache.W = p.W; cache.stride = p.stride; cache.stem = p.stem;
     cache.dt = act_dtype;
   }
-  const size_t smem = 1024 + 2 * G_ABUF_BYTES + G_HRING * G_HALO_BYTES + G_MAX_KB * 32 * 32 + sizeof(GSync);
+  p.halo_stride = (p.halo_bytes + 1023u) & ~1023u;
+  p.abuf_bytes = (uint32_t)p.n_kb * G_KB_BYTES;
+  const size_t kMaxSmem = 232448;
+  const size_t fixed = 1024 + G_MAX_KB * 32 * 32 + sizeof(GSync);
+  static const char* env_ab = getenv("DRNB200_G_ABUF");      // A/B knob: number of im2col buffers (2..4)
+  p.n_abuf = env_ab ? std::max(2, std::min(G_MAX_ABUF, atoi(env_ab))) : G_MAX_ABUF;
+  p.ring = (int)std::min<size_t>(G_HRING, (kMaxSmem - fixed - (size_t)p.n_abuf * p.abuf_bytes) / p.halo_stride);
+  if (p.ring < 2) { set_error("conv_gather: buffers do not fit shared memory"); return DRNB200_E_ARG; }
+  const size_t smem = kMaxSmem;
   static bool attr_done[2] = {false, false};
   if (!attr_done[act_dtype]) {
     if (act_dtype == DRNB200_BF16)

@@ -1,0 +1,347 @@
+// conv_halo.cu — stride-1 3x3 convolutions with Cin <= 64 and Cout <= 64 where the tensor core reads the
+// filter taps as SHIFTED WINDOWS of one shared-memory halo tile (no im2col copy, no per-tap reload).
+//
+// Why: for the narrow layers (DRN layer1: 16->16 at full resolution, layer3: 64->64 at 1/4) the per-tap
+// TMA path of conv_tc.cu moves every input pixel L2->SM nine times and is bound by that traffic
+// (layer3: 0.23 ms per conv at batch 8 vs a 0.04 ms HBM floor).  Here one TMA box per tile brings the halo
+//   [16+2d rows][16 pixels][Cin channels]      (pixel rows of `pitch` = Cin*2 bytes, SWIZZLE_{32,64,128}B)
+// and tap (ky,kx) of the 8x16-pixel output tile is the UMMA A operand whose descriptor simply starts
+// (ky*d*16 + kx*d) pixel rows further: M row m = (ty, tx) -> 8-row group ty (stride = one halo row =
+// 16*pitch bytes, a multiple of the swizzle atom) and row tx inside it.  Measured on B200: the UMMA swizzle
+// XOR is taken from the ABSOLUTE shared-memory address bits (like TMA's), so a start that is not atom
+// aligned needs no compensation — the descriptor base-offset field must stay 0 (setting it to
+// (start >> 7) & 7 gives wrong results; DRNB200_HALO=1 reproduces that for the record).
+// Weights stay resident in shared memory for the whole CTA.
+// Orientation as MODE_P: M = 128 pixels (TMEM lanes), N = Cout (columns), K-step 16.
+// Roles (320 threads): warp 0 halo TMA producer, warp 1 TMEM alloc + MMA issue, warps 2-9 epilogue
+// (two groups of four warps take alternate tiles; BN affine + residual + ReLU, 16-byte vector accesses,
+// thread = pixel).  Four TMEM accumulator stages keep both groups and the MMA issuer busy.
+#include "conv_internal.cuh"
+#include <algorithm>
+#include <cudaTypedefs.h>
+#include <new>
+
+namespace drnb200 {
+
+constexpr int H_THREADS = 320;          // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int H_TW = 8, H_TH = 16;      // output tile (pixels)
+constexpr int H_WP = 16;                // halo row length in pixels (8 + 2*dil <= 16)
+constexpr int H_MAX_RING = 6;
+constexpr int H_ACC = 4;                // TMEM accumulator stages: the MMA -> epilogue -> MMA round trip is
+                                        // ~3000 cycles, far longer than a tile of these small layers
+constexpr uint32_t H_TMEM_COLS = 256;   // 4 accumulators x 64 columns
+
+struct HaloParams {
+  const void* x;
+  const void* residual;
+  void* y;
+  const uint8_t* w_packed;   // n_kb tiles of Cout x Cin, K-major swizzled rows of `pitch` bytes
+  const int32_t* kblk;       // live taps
+  const float* scale;
+  const float* shift;
+  int n_kb, N, H, W, Cin, Cout, dil, relu, has_res;
+  int tiles_x, tiles_y, total_tiles, halo_h, ring;
+  uint32_t pitch, halo_bytes, w_tile_bytes, idesc, base_off_mode;
+};
+
+struct __align__(16) HSync {
+  uint64_t h_full[H_MAX_RING], h_empty[H_MAX_RING], t_full[H_ACC], t_empty[H_ACC], w_full;
+  uint32_t tmem_base;
+  int32_t taps[9];
+  alignas(16) float scale[64];
+  alignas(16) float shift[64];
+};
+
+struct HTile { int n, ox0, oy0; };
+__device__ __forceinline__ HTile h_decode(const HaloParams& p, int t) {
+  HTile c;
+  const int txi = t % p.tiles_x; t /= p.tiles_x;
+  const int tyi = t % p.tiles_y;
+  c.n = t / p.tiles_y;
+  c.ox0 = txi * H_TW; c.oy0 = tyi * H_TH;
+  return c;
+}
+
+// K-major swizzled descriptor with explicit 8-row-group stride and base offset
+__device__ __forceinline__ uint64_t umma_desc_ex(uint32_t addr, uint32_t pitch, uint32_t sbo, uint32_t base_off) {
+  const uint64_t layout = (pitch == 128u) ? 2ull : (pitch == 64u ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_off & 7u) << 49;
+  d |= layout << 61;
+  return d;
+}
+
+template <int DT, int KSTEPS>
+__global__ void __launch_bounds__(H_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* halo = smem;                                            // ring x halo_bytes (1024-multiple)
+  uint8_t* wsm = smem + (size_t)p.ring * p.halo_bytes;             // n_kb x w_tile_bytes
+  HSync* sync = reinterpret_cast<HSync*>(wsm + ((9u * p.w_tile_bytes + 1023u) & ~1023u));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int b = 0; b < p.ring; ++b) { mbar_init(&sync->h_full[b], 1); mbar_init(&sync->h_empty[b], 1); }
+    for (int a = 0; a < H_ACC; ++a) { mbar_init(&sync->t_full[a], 1); mbar_init(&sync->t_empty[a], 4); }
+    mbar_init(&sync->w_full, 1);
+    for (int k = 0; k < 9; ++k) sync->taps[k] = k < p.n_kb ? __ldg(p.kblk + k) : 0;
+    mbar_fence_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 64) {     // BN affine -> shared memory (read by every pixel thread)
+    const int ch = threadIdx.x - 64;
+    sync->scale[ch] = ch < p.Cout ? __ldg(p.scale + ch) : 0.f;
+    sync->shift[ch] = ch < p.Cout ? __ldg(p.shift + ch) : 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc(&sync->tmem_base, H_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sync->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      // resident weights: one bulk copy
+      mbar_arrive_expect_tx(&sync->w_full, (uint32_t)p.n_kb * p.w_tile_bytes);
+      bulk_load(p.w_packed, &sync->w_full, wsm, (uint32_t)p.n_kb * p.w_tile_bytes);
+      int i = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+        const int b = i % p.ring;
+        const HTile c = h_decode(p, t);
+        mbar_wait(&sync->h_empty[b], ((uint32_t)(i / p.ring) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&sync->h_full[b], p.halo_bytes);
+        // tensor {Cin, W, H, N}; box {Cin, 16, 16+2d, 1}; zero fill outside the image = conv padding
+        tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_bytes, 0, c.ox0 - p.dil,
+                    c.oy0 - p.dil, c.n);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      mbar_wait(&sync->w_full, 0);
+      // The single issuing thread is the bottleneck of these small-N layers (measured: ~100 cycles per
+      // MMA when descriptors were rebuilt in the loop), so everything loop-invariant is hoisted: the
+      // descriptor high words, the per-tap start offsets (in 16-byte units) and the weight tile stride.
+      const uint32_t row_bytes = (uint32_t)H_WP * p.pitch;          // one halo row = 8-row-group stride
+      const uint64_t a_hi = umma_desc_ex(0u, p.pitch, row_bytes, 0u);
+      const uint64_t b_hi = umma_desc_ex(0u, p.pitch, 8u * p.pitch, 0u);
+      const uint32_t w16 = smem_u32(wsm) >> 4, wt16 = p.w_tile_bytes >> 4;
+      uint32_t a_off16[9];
+#pragma unroll
+      for (int kb = 0; kb < 9; ++kb) {
+        const int tap = sync->taps[kb];
+        const int ky = tap / 3, kx = tap - ky * 3;
+        a_off16[kb] = ((uint32_t)(ky * p.dil) * row_bytes + (uint32_t)(kx * p.dil) * p.pitch) >> 4;
+      }
+      const int n_kb = p.n_kb;
+      int i = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+        const int b = i % p.ring, acc = i % H_ACC;
+        mbar_wait(&sync->h_full[b], (uint32_t)(i / p.ring) & 1u);
+        mbar_wait(&sync->t_empty[acc], ((uint32_t)(i / H_ACC) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t h16 = smem_u32(halo + (size_t)b * p.halo_bytes) >> 4;
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 64u;
+#pragma unroll
+        for (int kb = 0; kb < 9; ++kb) {
+          if (kb < n_kb) {
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks)
+              umma_f16(d_tmem, a_hi | (uint64_t)(h16 + a_off16[kb] + 2u * ks),
+                       b_hi | (uint64_t)(w16 + (uint32_t)kb * wt16 + 2u * ks), p.idesc,
+                       (kb > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&sync->h_empty[b]);
+        umma_commit(&sync->t_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;                // epilogue group 0/1 takes tiles i = grp, grp+2, ...
+    const int m = q * 32 + lane;                    // TMEM lane = pixel (ty = m / 8, tx = m % 8)
+    const uint16_t* res16 = reinterpret_cast<const uint16_t*>(p.residual);
+    uint16_t* y16 = reinterpret_cast<uint16_t*>(p.y);
+    for (int i = grp, t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += 2 * gridDim.x, i += 2) {
+      const int acc = i % H_ACC;
+      const HTile c = h_decode(p, t);
+      const int ox = c.ox0 + (m & (H_TW - 1)), oy = c.oy0 + (m >> 3);
+      const bool valid = ox < p.W && oy < p.H;
+      const size_t off0 = (((size_t)c.n * p.H + oy) * p.W + ox) * p.Cout;
+      // the residual of this pixel (<= 128 B) is requested before the accumulator wait so that its
+      // latency overlaps the MMAs instead of serialising behind every 16-channel group
+      uint4 rv[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        rv[g] = make_uint4(0u, 0u, 0u, 0u);
+        if (p.has_res && valid && g * 8 < p.Cout) rv[g] = __ldg(reinterpret_cast<const uint4*>(res16 + off0) + g);
+      }
+      mbar_wait(&sync->t_full[acc], (uint32_t)(i / H_ACC) & 1u);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t)acc * 64u + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int cbi = 0; cbi < 4; ++cbi) {
+        const int cb = cbi * 16;
+        if (cb < p.Cout) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + (uint32_t)cb, v);
+          tmem_ld_wait();
+          if (valid) {
+            const uint32_t rw[8] = {rv[2 * cbi].x, rv[2 * cbi].y, rv[2 * cbi].z, rv[2 * cbi].w,
+                                    rv[2 * cbi + 1].x, rv[2 * cbi + 1].y, rv[2 * cbi + 1].z, rv[2 * cbi + 1].w};
+            uint32_t w[8];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 sc = *reinterpret_cast<const float4*>(&sync->scale[cb + 4 * e4]);
+              const float4 sh = *reinterpret_cast<const float4*>(&sync->shift[cb + 4 * e4]);
+              const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int e = 2 * e4 + h2;     // output word e holds channels cb+2e, cb+2e+1
+                float a = fmaf(__uint_as_float(v[2 * e]), scv[2 * h2], shv[2 * h2]) +
+                          Act<DT>::to_f32((uint16_t)(rw[e] & 0xFFFFu));
+                float d = fmaf(__uint_as_float(v[2 * e + 1]), scv[2 * h2 + 1], shv[2 * h2 + 1]) +
+                          Act<DT>::to_f32((uint16_t)(rw[e] >> 16));
+                if (p.relu) { a = fmaxf(a, 0.f); d = fmaxf(d, 0.f); }
+                w[e] = (uint32_t)Act<DT>::from_f32(a) | ((uint32_t)Act<DT>::from_f32(d) << 16);
+              }
+            }
+            uint4* o = reinterpret_cast<uint4*>(y16 + off0 + cb);
+            o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sync->t_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, H_TMEM_COLS);
+  }
+}
+
+struct HMapCache {
+  const void* ptr = nullptr;
+  CUtensorMap map;
+};
+
+static PFN_cuTensorMapEncodeTiled_v12000 h_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+  return fn;
+}
+
+bool conv_halo_supported(const drnb200_conv_desc& d) {
+  // DRNB200_HALO=0 disables the path (A/B measurements); 1 = set the descriptor base offset (diagnostic, wrong)
+  static const char* env = getenv("DRNB200_HALO");
+  if (env && env[0] == '0') return false;
+  return d.ksize == 3 && d.stride == 1 && d.dilation >= 1 && d.dilation <= 4 && d.Cin == d.tile_ci &&
+         (d.Cin == 16 || d.Cin == 32 || d.Cin == 64) && d.tile_o == d.Cout && d.Cout % 16 == 0 && d.Cout <= 64 &&
+         !d.out_f32;
+}
+
+int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
+  const ConvParams& c = plan->p;
+  const drnb200_conv_desc& d = plan->d;
+  HaloParams p{};
+  p.x = c.x; p.residual = c.residual; p.y = c.y; p.w_packed = c.w_packed; p.kblk = c.kblk;
+  p.scale = c.scale; p.shift = c.shift;
+  p.n_kb = plan->h_row_ptr[1];
+  if (p.n_kb == 0) return conv_direct_launch(plan, st);   // everything pruned: y = act(shift + res)
+  p.N = c.N; p.H = c.H; p.W = c.W; p.Cin = c.Cin; p.Cout = c.Cout; p.dil = c.dil; p.relu = c.relu;
+  p.has_res = c.has_res;
+  p.pitch = (uint32_t)c.Cin * 2u;
+  p.halo_h = H_TH + 2 * c.dil;
+  p.halo_bytes = (uint32_t)p.halo_h * H_WP * p.pitch;
+  p.halo_bytes = (p.halo_bytes + 1023u) & ~1023u;
+  p.w_tile_bytes = (uint32_t)c.Cout * p.pitch;
+  p.tiles_x = (c.W + H_TW - 1) / H_TW;
+  p.tiles_y = (c.H + H_TH - 1) / H_TH;
+  p.total_tiles = c.N * p.tiles_x * p.tiles_y;
+  p.idesc = umma_idesc_f16(128, c.Cout, d.act_dtype);
+  static const char* env = getenv("DRNB200_HALO");
+  p.base_off_mode = (env && env[0] == '1') ? 1u : 0u;
+  const size_t kMaxSmem = 232448;
+  const size_t fixed = 1024 + ((9u * p.w_tile_bytes + 1023u) & ~1023u) + sizeof(HSync);
+  p.ring = (int)std::min<size_t>(H_MAX_RING, (kMaxSmem - fixed) / p.halo_bytes);
+  if (p.ring < 2) { set_error("conv_halo: halo tile does not fit shared memory"); return DRNB200_E_ARG; }
+
+  static_assert(sizeof(HMapCache) <= sizeof(plan->gather_cache), "halo cache storage too small");
+  HMapCache* cache = reinterpret_cast<HMapCache*>(plan->gather_cache);
+  if (!plan->gather_cache_init) { new (cache) HMapCache(); plan->gather_cache_init = true; }
+  if (cache->ptr != p.x) {
+    auto fn = h_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return DRNB200_E_CUDA; }
+    cuuint64_t gdim[4] = {(cuuint64_t)c.Cin, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
+    cuuint64_t gstr[3] = {(cuuint64_t)c.Cin * 2, (cuuint64_t)c.W * c.Cin * 2, (cuuint64_t)c.H * c.W * c.Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)c.Cin, (cuuint32_t)H_WP, (cuuint32_t)p.halo_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMapSwizzle sw = p.pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : p.pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(&cache->map, d.act_dtype == DRNB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                              : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                    4, const_cast<void*>(p.x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(halo) failed with CUresult %d (Cin=%d W=%d H=%d N=%d)", (int)r, c.Cin, c.W,
+                c.H, c.N);
+      return DRNB200_E_CUDA;
+    }
+    cache->ptr = p.x;
+  }
+  int dev = 0, sms = 148;
+  DRN_CUDA(cudaGetDevice(&dev));
+  DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = std::min(p.total_tiles, sms);
+  if (grid == 0) return DRNB200_OK;
+  const int ks = (int)(p.pitch / 32u);
+#define DRN_HALO_LAUNCH(DT, KS)                                                                           \
+  do {                                                                                                    \
+    static bool attr = false;                                                                             \
+    if (!attr) {                                                                                          \
+      DRN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<DT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)kMaxSmem));                                                      \
+      attr = true;                                                                                        \
+    }                                                                                                     \
+    conv_halo_kernel<DT, KS><<<grid, H_THREADS, kMaxSmem, st>>>(cache->map, p);                           \
+  } while (0)
+  if (d.act_dtype == DRNB200_BF16) {
+    if (ks == 4) DRN_HALO_LAUNCH(DRNB200_BF16, 4);
+    else if (ks == 2) DRN_HALO_LAUNCH(DRNB200_BF16, 2);
+    else DRN_HALO_LAUNCH(DRNB200_BF16, 1);
+  } else {
+    if (ks == 4) DRN_HALO_LAUNCH(DRNB200_F16, 4);
+    else if (ks == 2) DRN_HALO_LAUNCH(DRNB200_F16, 2);
+    else DRN_HALO_LAUNCH(DRNB200_F16, 1);
+  }
+#undef DRN_HALO_LAUNCH
+  DRN_CUDA(cudaGetLastError());
+  return DRNB200_OK;
+}
+
+}  // namespace drnb200

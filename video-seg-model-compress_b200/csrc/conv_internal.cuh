@@ -59,4 +59,7 @@ int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st);
 bool conv_gather_supported(const drnb200_conv_desc& d);     // 16-channel 3x3 layers (conv_gather.cu)
 int conv_gather_launch(drnb200_conv_plan* plan, cudaStream_t st);
 constexpr int TC_MODE_GATHER = 3;
+bool conv_halo_supported(const drnb200_conv_desc& d);       // stride-1 3x3, Cin,Cout <= 64 (conv_halo.cu)
+int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st);
+constexpr int TC_MODE_HALO = 4;
 }  // namespace drnb200

@@ -52,9 +52,14 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
   plan->tile_macs = n_live * (int64_t)p.tile_o * p.tile_ci * (int64_t)p.N * p.OH * p.OW;
 
   plan->impl = 0;
+  // 16-channel layers: im2col-gather kernel (its halo TMA box has long rows); other narrow stride-1
+  // layers: shifted-window halo kernel; everything else: per-tap TMA implicit GEMM
   if (d.impl != DRNB200_IMPL_DIRECT && conv_gather_supported(d)) {
     plan->impl = DRNB200_IMPL_TCGEN05;
     plan->tc_mode = TC_MODE_GATHER;
+  } else if (d.impl != DRNB200_IMPL_DIRECT && conv_halo_supported(d)) {
+    plan->impl = DRNB200_IMPL_TCGEN05;
+    plan->tc_mode = TC_MODE_HALO;
   } else if (d.impl != DRNB200_IMPL_DIRECT) {
     int rc = conv_tc_setup(plan);
     if (rc == DRNB200_OK) plan->impl = DRNB200_IMPL_TCGEN05;
@@ -87,6 +92,7 @@ extern "C" int drnb200_conv_forward(drnb200_conv_plan* plan, const void* x_nhwc,
   plan->p.y = y_nhwc;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->impl != DRNB200_IMPL_TCGEN05) return conv_direct_launch(plan, st);
+  if (plan->tc_mode == TC_MODE_HALO) return conv_halo_launch(plan, st);
   return plan->tc_mode == TC_MODE_GATHER ? conv_gather_launch(plan, st) : conv_tc_launch(plan, st);
 }
 
