@@ -52,7 +52,9 @@ struct GatherParams {
   uint32_t idesc;
 };
 
-struct __align__(8) GSync {
+struct __align__(16) GSync {
+  alignas(16) float scale[32];
+  alignas(16) float shift[32];
   uint64_t h_full[G_HRING], h_empty[G_HRING], a_full[G_MAX_ABUF], a_empty[G_MAX_ABUF],
       t_full[G_ACC], t_empty[G_ACC];
   uint32_t tmem_base, pad;
@@ -125,6 +127,11 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
     tmem_alloc(&sync->tmem_base, G_TMEM_COLS);
     tmem_relinquish();
   }
+  if (tid < 32) {   // BN affine -> shared memory: with ~all of the SM's storage carved out as shared memory
+                    // there is no L1 left, and 32 global loads per pixel thread per tile would go to L2
+    sync->scale[tid] = tid < p.Cout ? __ldg(p.scale + tid) : 0.f;
+    sync->shift[tid] = tid < p.Cout ? __ldg(p.shift + tid) : 0.f;
+  }
   {  // resident weights: plain 16-byte copies (a few KB, once per CTA)
     const int n16 = p.n_kb * p.Cout * 2;
     const uint4* src = reinterpret_cast<const uint4*>(p.w_packed);
@@ -141,11 +148,11 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
   if (warp == 9) {
     // ================================================================= halo TMA producer
     if (lane == 0) {
-      int i = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-        const int b = i % p.ring;
+      int b = 0;
+      uint32_t bph = 0;                       // ring slot / phase kept incrementally (no div/mod per tile)
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const GTile c = g_decode(p, t);
-        mbar_wait(&sync->h_empty[b], ((uint32_t)(i / p.ring) & 1u) ^ 1u);
+        mbar_wait(&sync->h_empty[b], bph ^ 1u);
         mbar_arrive_expect_tx(&sync->h_full[b], p.halo_bytes);
         if (p.stem)   // tensor {W, H, 3, N} fp32, box {40, 10, 3, 1}; x origin ox0-4 keeps the box 16-byte aligned
           tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_stride, c.ox0 - 4, c.oy0 - 3, 0, c.n);
@@ -154,6 +161,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
                       // pixel is its own 32-byte TMA row and the load is row-rate bound: ~5 cycles per row.)
           tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_stride, (c.ox0 * p.stride - 1) * 4,
                       c.oy0 * p.stride - 1, c.n, 0);
+        if (++b == p.ring) { b = 0; bph ^= 1u; }
       }
     }
     __syncwarp();
@@ -164,10 +172,11 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
       const uint64_t d_hi = umma_smem_desc(0u, 32);
       const uint32_t w16 = smem_u32(wsm) >> 4, wk16 = (uint32_t)w_kb_bytes >> 4;
       const int n_kb = p.n_kb;
-      int i = 0;
+      int i = 0, b = 0;
+      uint32_t bph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-        const int b = i % p.n_abuf, ta = i % G_ACC;
-        mbar_wait(&sync->a_full[b], (uint32_t)(i / p.n_abuf) & 1u);
+        const int ta = i % G_ACC;
+        mbar_wait(&sync->a_full[b], bph);
         mbar_wait(&sync->t_empty[ta], ((uint32_t)(i / G_ACC) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t a16 = smem_u32(abuf + (size_t)b * p.abuf_bytes) >> 4;
@@ -178,6 +187,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
                      d_hi | (uint64_t)(w16 + kb * wk16), p.idesc, kb > 0 ? 1u : 0u);
         umma_commit(&sync->a_empty[b]);
         umma_commit(&sync->t_full[ta]);
+        if (++b == p.n_abuf) { b = 0; bph ^= 1u; }
       }
     }
     __syncwarp();
@@ -203,12 +213,14 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
         if (valid) {
           uint32_t w[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float a = fmaf(__uint_as_float(v[2 * e]), __ldg(p.scale + cb + 2 * e), __ldg(p.shift + cb + 2 * e));
-            float d = fmaf(__uint_as_float(v[2 * e + 1]), __ldg(p.scale + cb + 2 * e + 1),
-                           __ldg(p.shift + cb + 2 * e + 1));
-            if (p.relu) { a = fmaxf(a, 0.f); d = fmaxf(d, 0.f); }
-            w[e] = (uint32_t)Act<DT>::from_f32(a) | ((uint32_t)Act<DT>::from_f32(d) << 16);
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 sc = *reinterpret_cast<const float4*>(&sync->scale[cb + 4 * e4]);
+            const float4 sh = *reinterpret_cast<const float4*>(&sync->shift[cb + 4 * e4]);
+            float a0 = fmaf(__uint_as_float(v[4 * e4]), sc.x, sh.x), a1 = fmaf(__uint_as_float(v[4 * e4 + 1]), sc.y, sh.y);
+            float a2 = fmaf(__uint_as_float(v[4 * e4 + 2]), sc.z, sh.z), a3 = fmaf(__uint_as_float(v[4 * e4 + 3]), sc.w, sh.w);
+            if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+            w[2 * e4] = (uint32_t)Act<DT>::from_f32(a0) | ((uint32_t)Act<DT>::from_f32(a1) << 16);
+            w[2 * e4 + 1] = (uint32_t)Act<DT>::from_f32(a2) | ((uint32_t)Act<DT>::from_f32(a3) << 16);
           }
           uint4* o = reinterpret_cast<uint4*>(yp + cb);
           o[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -231,11 +243,11 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
         tap_off[kb] = ((tap / 3) * p.halo_w + (tap % 3)) * 32;
       }
     }
-    int i = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-      const int b = i % p.n_abuf, hb = i % p.ring;
-      mbar_wait(&sync->h_full[hb], (uint32_t)(i / p.ring) & 1u);    // halo of this tile has landed
-      mbar_wait(&sync->a_empty[b], ((uint32_t)(i / p.n_abuf) & 1u) ^ 1u);   // MMAs that read this buffer retired
+    int b = 0, hb = 0;
+    uint32_t bph = 0, hph = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(&sync->h_full[hb], hph);          // halo of this tile has landed
+      mbar_wait(&sync->a_empty[b], bph ^ 1u);     // the MMAs that read this im2col buffer have retired
       const uint8_t* h = halo + (size_t)hb * p.halo_stride;
       uint8_t* a = abuf + (size_t)b * p.abuf_bytes;
       if (!p.stem) {
@@ -264,6 +276,8 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
         mbar_arrive(&sync->a_full[b]);
         mbar_arrive(&sync->h_empty[hb]);     // halo buffer may be refilled
       }
+      if (++b == p.n_abuf) { b = 0; bph ^= 1u; }
+      if (++hb == p.ring) { hb = 0; hph ^= 1u; }
     }
   }
 
@@ -342,18 +356,18 @@ static int gather_launch(GatherParams& p, int act_dtype, GMapCache& cache, cudaS
   const size_t kMaxSmem = 232448;
   const size_t fixed = 1024 + G_MAX_KB * 32 * 32 + sizeof(GSync);
   static const char* env_ab = getenv("DRNB200_G_ABUF");      // A/B knob: number of im2col buffers (2..4)
-  p.n_abuf = env_ab ? std::max(2, std::min(G_MAX_ABUF, atoi(env_ab))) : G_MAX_ABUF;
+  p.n_abuf = env_ab ? std::max(2, std::min(G_MAX_ABUF, atoi(env_ab))) : 3;
   p.ring = (int)std::min<size_t>(G_HRING, (kMaxSmem - fixed - (size_t)p.n_abuf * p.abuf_bytes) / p.halo_stride);
   if (p.ring < 2) { set_error("conv_gather: buffers do not fit shared memory"); return DRNB200_E_ARG; }
-  const size_t smem = kMaxSmem;
+  const size_t smem = fixed + (size_t)p.n_abuf * p.abuf_bytes + (size_t)p.ring * p.halo_stride;
   static bool attr_done[2] = {false, false};
   if (!attr_done[act_dtype]) {
     if (act_dtype == DRNB200_BF16)
       DRN_CUDA(cudaFuncSetAttribute(conv_gather_kernel<DRNB200_BF16>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     else
       DRN_CUDA(cudaFuncSetAttribute(conv_gather_kernel<DRNB200_F16>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     attr_done[act_dtype] = true;
   }
   int dev = 0, sms = 148;

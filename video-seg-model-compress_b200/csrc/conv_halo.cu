@@ -114,15 +114,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
       // resident weights: one bulk copy
       mbar_arrive_expect_tx(&sync->w_full, (uint32_t)p.n_kb * p.w_tile_bytes);
       bulk_load(p.w_packed, &sync->w_full, wsm, (uint32_t)p.n_kb * p.w_tile_bytes);
-      int i = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-        const int b = i % p.ring;
+      int b = 0;
+      uint32_t bph = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const HTile c = h_decode(p, t);
-        mbar_wait(&sync->h_empty[b], ((uint32_t)(i / p.ring) & 1u) ^ 1u);
+        mbar_wait(&sync->h_empty[b], bph ^ 1u);
         mbar_arrive_expect_tx(&sync->h_full[b], p.halo_bytes);
         // tensor {Cin, W, H, N}; box {Cin, 16, 16+2d, 1}; zero fill outside the image = conv padding
         tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_bytes, 0, c.ox0 - p.dil,
                     c.oy0 - p.dil, c.n);
+        if (++b == p.ring) { b = 0; bph ^= 1u; }
       }
     }
     __syncwarp();
@@ -145,10 +146,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
         a_off16[kb] = ((uint32_t)(ky * p.dil) * row_bytes + (uint32_t)(kx * p.dil) * p.pitch) >> 4;
       }
       const int n_kb = p.n_kb;
-      int i = 0;
+      int i = 0, b = 0;
+      uint32_t bph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-        const int b = i % p.ring, acc = i % H_ACC;
-        mbar_wait(&sync->h_full[b], (uint32_t)(i / p.ring) & 1u);
+        const int acc = i % H_ACC;
+        mbar_wait(&sync->h_full[b], bph);
         mbar_wait(&sync->t_empty[acc], ((uint32_t)(i / H_ACC) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t h16 = smem_u32(halo + (size_t)b * p.halo_bytes) >> 4;
@@ -165,6 +167,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
         }
         umma_commit(&sync->h_empty[b]);
         umma_commit(&sync->t_full[acc]);
+        if (++b == p.ring) { b = 0; bph ^= 1u; }
       }
     }
     __syncwarp();
