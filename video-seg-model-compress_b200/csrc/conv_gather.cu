@@ -10,9 +10,9 @@
 //   MODE stem: x NCHW float32 with 3 channels, 7x7, K = 147 padded to 160; the fp32 -> 16-bit conversion of
 //              the frame is fused into the expansion (drn.py:132-137; callers pass fp32 NCHW, semantic_seg.py:440)
 // GEMM orientation: M = 128 output pixels (TMEM lanes), N = Cout (16 or 32 columns), K-step = 16.
-// Roles (448 threads): warps 0-7 expand (256 threads), warp 8 allocates TMEM and issues the MMAs,
-// warp 9 issues the halo TMA loads up to G_HRING tiles ahead, warps 10-17 run the epilogue (two groups
-// of four warps on alternate tiles).
+// Roles (832 threads): warps 0-15 expand (512 threads; the expansion is latency/issue bound, so it gets
+// most of the CTA's warps), warp 16 allocates TMEM and issues the MMAs, warp 17 issues the halo TMA loads
+// up to G_HRING tiles ahead, warps 18-25 run the epilogue (two groups of four warps on alternate tiles).
 // A ring of halo buffers, two im2col buffers and two TMEM accumulators pipeline
 //   TMA(i+k) | expand(i+1) | MMA(i) | epilogue(i-1)   with every stage on its own warps.
 #include "conv_internal.cuh"
@@ -22,7 +22,9 @@
 
 namespace drnb200 {
 
-constexpr int G_THREADS = 576;          // 8 expand warps, MMA warp, TMA warp, 2 x 4 epilogue warps
+constexpr int G_EXP_WARPS = 16;         // expanding warps
+constexpr int G_W_MMA = G_EXP_WARPS, G_W_TMA = G_EXP_WARPS + 1, G_W_EPI = G_EXP_WARPS + 2;
+constexpr int G_THREADS = (G_EXP_WARPS + 2 + 8) * 32;
 constexpr int G_MAX_KB = 10;            // 9 taps, or 160/16 stem K-blocks
 constexpr int G_KB_BYTES = 128 * 32;    // one K-block of the im2col tile: 128 pixels x 16 elements
 constexpr int G_MAX_ABUF = 4;            // im2col buffers: expand(i+k) | MMA(i) — two were latency-bound (measured)
@@ -44,6 +46,7 @@ struct GatherParams {
   int stem;                  // 0: 3x3 over NHWC 16-channel input, 1: 7x7 over NCHW fp32 3-channel input
   int TW, TH, tw_shift;      // output tile (32x4; 16x8 for stride 2 so that the halo row fits one TMA box row)
   int tiles_x, tiles_y, total_tiles;
+  uint32_t magic_x, magic_y; // ceil(2^32 / tiles_{x,y}) for the division-free tile decode
   int halo_w, halo_h;        // 3x3: halo box in pixels
   uint32_t halo_bytes;       // TMA transaction bytes of one halo box
   uint32_t halo_stride;      // halo buffer pitch in shared memory (halo_bytes rounded up to 1 KB)
@@ -63,9 +66,10 @@ struct __align__(16) GSync {
 struct GTile { int n, ox0, oy0; };
 __device__ __forceinline__ GTile g_decode(const GatherParams& p, int t) {
   GTile c;
-  const int txi = t % p.tiles_x; t /= p.tiles_x;
-  const int tyi = t % p.tiles_y;
-  c.n = t / p.tiles_y;
+  const int q1 = p.tiles_x == 1 ? t : (int)__umulhi((uint32_t)t, p.magic_x);      // t / tiles_x
+  const int txi = t - q1 * p.tiles_x;
+  c.n = p.tiles_y == 1 ? q1 : (int)__umulhi((uint32_t)q1, p.magic_y);             // q1 / tiles_y
+  const int tyi = q1 - c.n * p.tiles_y;
   c.ox0 = txi * p.TW; c.oy0 = tyi * p.TH;
   return c;
 }
@@ -75,13 +79,12 @@ __host__ __device__ constexpr int stem_halo_off(int k) {
   return ((k / 49) * G_STEM_HH + (k % 49) / 7) * G_STEM_HW + (k % 7) + 1;
 }
 
-// chunks HALF, HALF+2, ... of one pixel's 160-element im2col row, offsets resolved at compile time
-template <int DT, int HALF>
+// chunks PART, PART+4, ... of one pixel's 160-element im2col row, offsets resolved at compile time
+template <int DT, int PART>
 __device__ __forceinline__ void stem_expand(const float* hp, uint8_t* a, int m) {
 #pragma unroll
-  for (int cc = 0; cc < G_MAX_KB; ++cc) {
-    constexpr int dummy = 0; (void)dummy;
-    const int c = 2 * cc + HALF;
+  for (int cc = 0; cc < G_MAX_KB / 2; ++cc) {
+    const int c = 4 * cc + PART;
     uint32_t w[4];
 #pragma unroll
     for (int e2 = 0; e2 < 4; ++e2) {
@@ -111,10 +114,10 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
     tma_prefetch_desc(&tmap_x);
     for (int b = 0; b < G_HRING; ++b) {
       mbar_init(&sync->h_full[b], 1);
-      mbar_init(&sync->h_empty[b], 8);    // one arrive per expanding warp
+      mbar_init(&sync->h_empty[b], G_EXP_WARPS);    // one arrive per expanding warp
     }
     for (int b = 0; b < G_MAX_ABUF; ++b) {
-      mbar_init(&sync->a_full[b], 8);
+      mbar_init(&sync->a_full[b], G_EXP_WARPS);
       mbar_init(&sync->a_empty[b], 1);
     }
     for (int b = 0; b < G_ACC; ++b) {
@@ -123,7 +126,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
     }
     mbar_fence_init();
   }
-  if (warp == 8) {
+  if (warp == G_W_MMA) {
     tmem_alloc(&sync->tmem_base, G_TMEM_COLS);
     tmem_relinquish();
   }
@@ -145,30 +148,30 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
   const uint32_t tmem_base = sync->tmem_base;
   const int w_kb_bytes = p.Cout * 32;
 
-  if (warp == 9) {
-    // ================================================================= halo TMA producer
-    if (lane == 0) {
+  if (warp == G_W_TMA) {
+    // ================================================================= halo TMA producer (warp-uniform loop)
+    {
       int b = 0;
       uint32_t bph = 0;                       // ring slot / phase kept incrementally (no div/mod per tile)
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const GTile c = g_decode(p, t);
         mbar_wait(&sync->h_empty[b], bph ^ 1u);
-        mbar_arrive_expect_tx(&sync->h_full[b], p.halo_bytes);
-        if (p.stem)   // tensor {W, H, 3, N} fp32, box {40, 10, 3, 1}; x origin ox0-4 keeps the box 16-byte aligned
-          tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_stride, c.ox0 - 4, c.oy0 - 3, 0, c.n);
-        else          // tensor {W*4, H, N, 1} of 8-byte elements (a pixel = 16 ch x 2 B = 4 elements), box
-                      // {halo_w*4, halo_h, 1, 1}: one box row per halo row.  (With a {16ch, px, rows} box every
-                      // pixel is its own 32-byte TMA row and the load is row-rate bound: ~5 cycles per row.)
-          tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_stride, (c.ox0 * p.stride - 1) * 4,
-                      c.oy0 * p.stride - 1, c.n, 0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sync->h_full[b], p.halo_bytes);
+          if (p.stem)   // tensor {W, H, 3, N} fp32, box {40, 10, 3, 1}; x origin ox0-4 keeps the box 16-byte aligned
+            tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_stride, c.ox0 - 4, c.oy0 - 3, 0, c.n);
+          else          // tensor {W*4, H, N, 1} of 8-byte elements (a pixel = 16 ch x 2 B = 4 elements), box
+                        // {halo_w*4, halo_h, 1, 1}: one box row per halo row
+            tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_stride, (c.ox0 * p.stride - 1) * 4,
+                        c.oy0 * p.stride - 1, c.n, 0);
+        }
+        __syncwarp();
         if (++b == p.ring) { b = 0; bph ^= 1u; }
       }
     }
-    __syncwarp();
-  } else if (warp == 8) {
-    // ================================================================= MMA issuer
-    if (lane == 0) {
-      // loop-invariant descriptor parts hoisted: the single issuing thread is the critical path here
+  } else if (warp == G_W_MMA) {
+    // ================================================================= MMA issuer (warp-uniform loop)
+    {
       const uint64_t d_hi = umma_smem_desc(0u, 32);
       const uint32_t w16 = smem_u32(wsm) >> 4, wk16 = (uint32_t)w_kb_bytes >> 4;
       const int n_kb = p.n_kb;
@@ -180,22 +183,24 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
         mbar_wait(&sync->t_empty[ta], ((uint32_t)(i / G_ACC) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t a16 = smem_u32(abuf + (size_t)b * p.abuf_bytes) >> 4;
+        if (elect_one()) {
 #pragma unroll
-        for (int kb = 0; kb < G_MAX_KB; ++kb)
-          if (kb < n_kb)
-            umma_f16(tmem_base + ta * 32u, d_hi | (uint64_t)(a16 + kb * (G_KB_BYTES >> 4)),
-                     d_hi | (uint64_t)(w16 + kb * wk16), p.idesc, kb > 0 ? 1u : 0u);
-        umma_commit(&sync->a_empty[b]);
-        umma_commit(&sync->t_full[ta]);
+          for (int kb = 0; kb < G_MAX_KB; ++kb)
+            if (kb < n_kb)
+              umma_f16(tmem_base + ta * 32u, d_hi | (uint64_t)(a16 + kb * (G_KB_BYTES >> 4)),
+                       d_hi | (uint64_t)(w16 + kb * wk16), p.idesc, kb > 0 ? 1u : 0u);
+          umma_commit(&sync->a_empty[b]);
+          umma_commit(&sync->t_full[ta]);
+        }
+        __syncwarp();
         if (++b == p.n_abuf) { b = 0; bph ^= 1u; }
       }
     }
-    __syncwarp();
-  } else if (warp >= 10) {
+  } else if (warp >= G_W_EPI) {
     // ================================================================= epilogue (warps 10..13)
     uint16_t* y16 = reinterpret_cast<uint16_t*>(p.y);
     const int q = warp & 3;                                // TMEM lane quarter of this warp
-    const int grp = (warp - 10) >> 2;                      // epilogue group 0/1 takes alternate tiles
+    const int grp = (warp - G_W_EPI) >> 2;                 // epilogue group 0/1 takes alternate tiles
     const int m = q * 32 + lane;                           // TMEM lane = pixel of the tile
     for (int i = grp, t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += 2 * gridDim.x, i += 2) {
       const int b = i % G_ACC;
@@ -234,13 +239,14 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
   } else {
     // ================================================================= expand
     // 3x3: byte offset of every live tap inside the halo (constant for the whole kernel)
-    int tap_off[9];
+    int tap_off[5];
 #pragma unroll
-    for (int kb = 0; kb < 9; ++kb) {
-      tap_off[kb] = 0;
+    for (int j = 0; j < 5; ++j) {
+      const int kb = 2 * j + (tid >> 8);
+      tap_off[j] = 0;
       if (!p.stem && kb < p.n_kb) {
         const int tap = __ldg(p.kblk + kb);
-        tap_off[kb] = ((tap / 3) * p.halo_w + (tap % 3)) * 32;
+        tap_off[j] = ((tap / 3) * p.halo_w + (tap % 3)) * 32;
       }
     }
     int b = 0, hb = 0;
@@ -251,24 +257,32 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
       const uint8_t* h = halo + (size_t)hb * p.halo_stride;
       uint8_t* a = abuf + (size_t)b * p.abuf_bytes;
       if (!p.stem) {
-        // thread = (pixel m, 16-byte half of its 16 channels); a K-block is one filter tap
-        const int m = tid >> 1, half = tid & 1;
+        // thread = (pixel m, 16-byte half of its 16 channels, tap parity); a K-block is one filter tap
+        const int m = (tid & 255) >> 1, half = tid & 1, tg = tid >> 8;
         const int hx = (m & (p.TW - 1)) * p.stride, hy = (m >> p.tw_shift) * p.stride;
         const uint8_t* src0 = h + ((size_t)hy * p.halo_w + hx) * 32 + half * 16;
         uint8_t* dst0 = a + swz_offset((uint32_t)m, (uint32_t)half, 32);
-        uint4 v[9];
+        uint4 v[5];
 #pragma unroll
-        for (int kb = 0; kb < 9; ++kb)
-          if (kb < p.n_kb) v[kb] = *reinterpret_cast<const uint4*>(src0 + tap_off[kb]);
+        for (int j = 0; j < 5; ++j) {
+          const int kb = 2 * j + tg;
+          if (kb < p.n_kb) v[j] = *reinterpret_cast<const uint4*>(src0 + tap_off[j]);
+        }
 #pragma unroll
-        for (int kb = 0; kb < 9; ++kb)
-          if (kb < p.n_kb) *reinterpret_cast<uint4*>(dst0 + kb * G_KB_BYTES) = v[kb];
+        for (int j = 0; j < 5; ++j) {
+          const int kb = 2 * j + tg;
+          if (kb < p.n_kb) *reinterpret_cast<uint4*>(dst0 + kb * G_KB_BYTES) = v[j];
+        }
       } else {
         // stem: thread = (pixel m, chunk parity); chunk c holds k = 8c .. 8c+7 (k = ci*49 + ky*7 + kx)
         const int m = tid & 127;
         const float* hp = reinterpret_cast<const float*>(h) + (m / G_STEM_TW) * G_STEM_HW + (m & (G_STEM_TW - 1));
-        if (tid < 128) stem_expand<DT, 0>(hp, a, m);
-        else stem_expand<DT, 1>(hp, a, m);
+        switch (tid >> 7) {                       // warp-uniform: 4 thread groups x 5 chunks each
+          case 0: stem_expand<DT, 0>(hp, a, m); break;
+          case 1: stem_expand<DT, 1>(hp, a, m); break;
+          case 2: stem_expand<DT, 2>(hp, a, m); break;
+          default: stem_expand<DT, 3>(hp, a, m); break;
+        }
       }
       fence_proxy_async_smem();              // im2col tile -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -283,7 +297,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == G_W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, G_TMEM_COLS);
   }
@@ -314,6 +328,12 @@ static int gather_launch(GatherParams& p, int act_dtype, GMapCache& cache, cudaS
   p.tiles_x = (p.OW + p.TW - 1) / p.TW;
   p.tiles_y = (p.OH + p.TH - 1) / p.TH;
   p.total_tiles = p.N * p.tiles_x * p.tiles_y;
+  if ((uint64_t)p.total_tiles * (uint64_t)std::max(p.tiles_x, p.tiles_y) >= (1ull << 32)) {
+    set_error("conv_gather: problem too large for the 32-bit tile decode");
+    return DRNB200_E_ARG;
+  }
+  p.magic_x = p.tiles_x == 1 ? 0u : (uint32_t)(((1ull << 32) + p.tiles_x - 1) / p.tiles_x);
+  p.magic_y = p.tiles_y == 1 ? 0u : (uint32_t)(((1ull << 32) + p.tiles_y - 1) / p.tiles_y);
   p.idesc = umma_idesc_f16(128, p.Cout, act_dtype);
   if (p.stem) {
     p.halo_w = G_STEM_HW; p.halo_h = G_STEM_HH;
@@ -382,6 +402,8 @@ static int gather_launch(GatherParams& p, int act_dtype, GMapCache& cache, cudaS
 }
 
 bool conv_gather_supported(const drnb200_conv_desc& d) {
+  static const char* env = getenv("DRNB200_GATHER");   // A/B knob: 0 = route 16-channel layers elsewhere
+  if (env && env[0] == '0') return false;
   return d.ksize == 3 && d.Cin == 16 && d.tile_ci == 16 && d.tile_o == d.Cout &&
          (d.Cout == 16 || d.Cout == 32) && d.dilation == 1 && (d.stride == 1 || d.stride == 2) &&
          !d.has_residual && !d.out_f32;

@@ -23,7 +23,11 @@
 
 namespace drnb200 {
 
-constexpr int H_THREADS = 320;          // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int H_EPI_GROUPS = 2;         // epilogue groups of four warps, one tile each, round-robin
+constexpr int H_MMA_WARPS = 2;          // MMA-issuing warps on alternate tiles: the per-tile wait/commit
+                                        // latency of one issuer (~800 cycles) bounded the small layers
+constexpr int H_W_EPI = 1 + H_MMA_WARPS;
+constexpr int H_THREADS = (H_W_EPI + 4 * H_EPI_GROUPS) * 32;
 constexpr int H_TW = 8, H_TH = 16;      // output tile (pixels)
 constexpr int H_WP = 16;                // halo row length in pixels (8 + 2*dil <= 16)
 constexpr int H_MAX_RING = 6;
@@ -41,7 +45,9 @@ struct HaloParams {
   const float* shift;
   int n_kb, N, H, W, Cin, Cout, dil, relu, has_res;
   int tiles_x, tiles_y, total_tiles, halo_h, ring;
+  uint32_t magic_x, magic_y;   // ceil(2^32 / tiles_{x,y}): exact quotients by __umulhi for t < 2^32 / divisor
   uint32_t pitch, halo_bytes, w_tile_bytes, idesc, base_off_mode;
+  int dbg;                   // diagnostics (DRNB200_DBG): 1 = issue one tap only, 2 = skip the global stores
 };
 
 struct __align__(16) HSync {
@@ -55,9 +61,10 @@ struct __align__(16) HSync {
 struct HTile { int n, ox0, oy0; };
 __device__ __forceinline__ HTile h_decode(const HaloParams& p, int t) {
   HTile c;
-  const int txi = t % p.tiles_x; t /= p.tiles_x;
-  const int tyi = t % p.tiles_y;
-  c.n = t / p.tiles_y;
+  const int q1 = p.tiles_x == 1 ? t : (int)__umulhi((uint32_t)t, p.magic_x);      // t / tiles_x
+  const int txi = t - q1 * p.tiles_x;
+  c.n = p.tiles_y == 1 ? q1 : (int)__umulhi((uint32_t)q1, p.magic_y);             // q1 / tiles_y
+  const int tyi = q1 - c.n * p.tiles_y;
   c.ox0 = txi * H_TW; c.oy0 = tyi * H_TH;
   return c;
 }
@@ -110,30 +117,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      // resident weights: one bulk copy
-      mbar_arrive_expect_tx(&sync->w_full, (uint32_t)p.n_kb * p.w_tile_bytes);
-      bulk_load(p.w_packed, &sync->w_full, wsm, (uint32_t)p.n_kb * p.w_tile_bytes);
+    {
+      // warp-uniform loop, single elected lane issues (see the MMA warp for why)
+      if (elect_one()) {     // resident weights: one bulk copy
+        mbar_arrive_expect_tx(&sync->w_full, (uint32_t)p.n_kb * p.w_tile_bytes);
+        bulk_load(p.w_packed, &sync->w_full, wsm, (uint32_t)p.n_kb * p.w_tile_bytes);
+      }
       int b = 0;
       uint32_t bph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const HTile c = h_decode(p, t);
         mbar_wait(&sync->h_empty[b], bph ^ 1u);
-        mbar_arrive_expect_tx(&sync->h_full[b], p.halo_bytes);
-        // tensor {Cin, W, H, N}; box {Cin, 16, 16+2d, 1}; zero fill outside the image = conv padding
-        tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_bytes, 0, c.ox0 - p.dil,
-                    c.oy0 - p.dil, c.n);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sync->h_full[b], p.halo_bytes);
+          // tensor {Cin, W, H, N}; box {Cin, 16, 16+2d, 1}; zero fill outside the image = conv padding
+          tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_bytes, 0, c.ox0 - p.dil,
+                      c.oy0 - p.dil, c.n);
+        }
+        __syncwarp();
         if (++b == p.ring) { b = 0; bph ^= 1u; }
       }
     }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+  } else if (warp < H_W_EPI) {
+    // ===================================================================== MMA issuers (warps 1..H_MMA_WARPS)
+    // The whole warp runs this loop with warp-uniform control flow and values; only the tcgen05 issue is
+    // predicated on one elected lane.  Inside an `if (lane == 0)` region nothing is provably uniform, so
+    // every descriptor went through R2UR (measured ~49 cycles per MMA + ~1000 cycles per tile); here the
+    // descriptors live in uniform registers.
+    {
       mbar_wait(&sync->w_full, 0);
-      // The single issuing thread is the bottleneck of these small-N layers (measured: ~100 cycles per
-      // MMA when descriptors were rebuilt in the loop), so everything loop-invariant is hoisted: the
-      // descriptor high words, the per-tap start offsets (in 16-byte units) and the weight tile stride.
       const uint32_t row_bytes = (uint32_t)H_WP * p.pitch;          // one halo row = 8-row-group stride
       const uint64_t a_hi = umma_desc_ex(0u, p.pitch, row_bytes, 0u);
       const uint64_t b_hi = umma_desc_ex(0u, p.pitch, 8u * p.pitch, 0u);
@@ -145,40 +157,45 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
         const int ky = tap / 3, kx = tap - ky * 3;
         a_off16[kb] = ((uint32_t)(ky * p.dil) * row_bytes + (uint32_t)(kx * p.dil) * p.pitch) >> 4;
       }
-      const int n_kb = p.n_kb;
-      int i = 0, b = 0;
-      uint32_t bph = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      const int n_kb = p.dbg == 1 ? 1 : p.n_kb;
+      const int mw = warp - 1;                               // this warp takes tiles i = mw, mw + H_MMA_WARPS, ...
+      int i = mw, b = mw % p.ring;
+      uint32_t bph = (uint32_t)(mw / p.ring) & 1u;
+      for (int t = blockIdx.x + mw * gridDim.x; t < p.total_tiles; t += H_MMA_WARPS * gridDim.x, i += H_MMA_WARPS) {
         const int acc = i % H_ACC;
         mbar_wait(&sync->h_full[b], bph);
         mbar_wait(&sync->t_empty[acc], ((uint32_t)(i / H_ACC) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t h16 = smem_u32(halo + (size_t)b * p.halo_bytes) >> 4;
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 64u;
+        if (elect_one()) {
 #pragma unroll
-        for (int kb = 0; kb < 9; ++kb) {
-          if (kb < n_kb) {
+          for (int kb = 0; kb < 9; ++kb) {
+            if (kb < n_kb) {
 #pragma unroll
-            for (int ks = 0; ks < KSTEPS; ++ks)
-              umma_f16(d_tmem, a_hi | (uint64_t)(h16 + a_off16[kb] + 2u * ks),
-                       b_hi | (uint64_t)(w16 + (uint32_t)kb * wt16 + 2u * ks), p.idesc,
-                       (kb > 0 || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < KSTEPS; ++ks)
+                umma_f16(d_tmem, a_hi | (uint64_t)(h16 + a_off16[kb] + 2u * ks),
+                         b_hi | (uint64_t)(w16 + (uint32_t)kb * wt16 + 2u * ks), p.idesc,
+                         (kb > 0 || ks > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(&sync->h_empty[b]);
+          umma_commit(&sync->t_full[acc]);
         }
-        umma_commit(&sync->h_empty[b]);
-        umma_commit(&sync->t_full[acc]);
-        if (++b == p.ring) { b = 0; bph ^= 1u; }
+        __syncwarp();
+        b += H_MMA_WARPS;
+        if (b >= p.ring) { b -= p.ring; bph ^= 1u; }
       }
     }
-    __syncwarp();
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;                // epilogue group 0/1 takes tiles i = grp, grp+2, ...
+    const int grp = (warp - H_W_EPI) >> 2;          // epilogue group g takes tiles i = g, g + H_EPI_GROUPS, ...
     const int m = q * 32 + lane;                    // TMEM lane = pixel (ty = m / 8, tx = m % 8)
     const uint16_t* res16 = reinterpret_cast<const uint16_t*>(p.residual);
     uint16_t* y16 = reinterpret_cast<uint16_t*>(p.y);
-    for (int i = grp, t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += 2 * gridDim.x, i += 2) {
+    for (int i = grp, t = blockIdx.x + grp * gridDim.x; t < p.total_tiles;
+         t += H_EPI_GROUPS * gridDim.x, i += H_EPI_GROUPS) {
       const int acc = i % H_ACC;
       const HTile c = h_decode(p, t);
       const int ox = c.ox0 + (m & (H_TW - 1)), oy = c.oy0 + (m >> 3);
@@ -223,8 +240,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
               }
             }
             uint4* o = reinterpret_cast<uint4*>(y16 + off0 + cb);
-            o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            if (p.dbg != 2 || w[0] == 0x12345678u) {
+              o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
           }
         }
       }
@@ -286,9 +305,17 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   p.tiles_x = (c.W + H_TW - 1) / H_TW;
   p.tiles_y = (c.H + H_TH - 1) / H_TH;
   p.total_tiles = c.N * p.tiles_x * p.tiles_y;
+  if ((uint64_t)p.total_tiles * (uint64_t)std::max(p.tiles_x, p.tiles_y) >= (1ull << 32)) {
+    set_error("conv_halo: problem too large for the 32-bit tile decode");
+    return DRNB200_E_ARG;
+  }
+  p.magic_x = p.tiles_x == 1 ? 0u : (uint32_t)(((1ull << 32) + p.tiles_x - 1) / p.tiles_x);
+  p.magic_y = p.tiles_y == 1 ? 0u : (uint32_t)(((1ull << 32) + p.tiles_y - 1) / p.tiles_y);
   p.idesc = umma_idesc_f16(128, c.Cout, d.act_dtype);
   static const char* env = getenv("DRNB200_HALO");
   p.base_off_mode = (env && env[0] == '1') ? 1u : 0u;
+  static const char* envd = getenv("DRNB200_DBG");
+  p.dbg = envd ? atoi(envd) : 0;
   const size_t kMaxSmem = 232448;
   const size_t fixed = 1024 + ((9u * p.w_tile_bytes + 1023u) & ~1023u) + sizeof(HSync);
   p.ring = (int)std::min<size_t>(H_MAX_RING, (kMaxSmem - fixed) / p.halo_bytes);

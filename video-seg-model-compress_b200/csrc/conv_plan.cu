@@ -52,14 +52,14 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
   plan->tile_macs = n_live * (int64_t)p.tile_o * p.tile_ci * (int64_t)p.N * p.OH * p.OW;
 
   plan->impl = 0;
-  // 16-channel layers: im2col-gather kernel (its halo TMA box has long rows); other narrow stride-1
-  // layers: shifted-window halo kernel; everything else: per-tap TMA implicit GEMM
-  if (d.impl != DRNB200_IMPL_DIRECT && conv_gather_supported(d)) {
-    plan->impl = DRNB200_IMPL_TCGEN05;
-    plan->tc_mode = TC_MODE_GATHER;
-  } else if (d.impl != DRNB200_IMPL_DIRECT && conv_halo_supported(d)) {
+  // narrow stride-1 3x3 layers (Cin, Cout <= 64): shifted-window halo kernel (no im2col copy);
+  // 16-channel stride-2 layers: im2col-gather kernel; everything else: per-tap TMA implicit GEMM
+  if (d.impl != DRNB200_IMPL_DIRECT && conv_halo_supported(d)) {
     plan->impl = DRNB200_IMPL_TCGEN05;
     plan->tc_mode = TC_MODE_HALO;
+  } else if (d.impl != DRNB200_IMPL_DIRECT && conv_gather_supported(d)) {
+    plan->impl = DRNB200_IMPL_TCGEN05;
+    plan->tc_mode = TC_MODE_GATHER;
   } else if (d.impl != DRNB200_IMPL_DIRECT) {
     int rc = conv_tc_setup(plan);
     if (rc == DRNB200_OK) plan->impl = DRNB200_IMPL_TCGEN05;

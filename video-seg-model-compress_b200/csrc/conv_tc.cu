@@ -116,7 +116,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    // (the whole warp runs the loop with warp-uniform values, one elected lane issues: inside an
+    //  `if (lane == 0)` region nothing is provably uniform and every operand goes through R2UR)
+    {
       uint32_t stage = 0, phase = 0;
       const int half = (p.taps == 9) ? 1 : 0;
       const uint32_t tx_bytes = p.w_tile_bytes + p.x_tile_bytes;
@@ -131,21 +133,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           uint8_t* sW = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sX = sW + p.w_stage_bytes;
           mbar_wait(&sync->empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&sync->full[stage], tx_bytes);
-          bulk_load(p.w_packed + (size_t)j * p.w_tile_bytes, &sync->full[stage], sW, p.w_tile_bytes);
-          tma_load_4d(&tmap, &sync->full[stage], sX, cib * p.tile_ci,
-                      c.ox0 * p.stride + (kx - half) * p.dil, c.oy0 * p.stride + (ky - half) * p.dil,
-                      c.n);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&sync->full[stage], tx_bytes);
+            bulk_load(p.w_packed + (size_t)j * p.w_tile_bytes, &sync->full[stage], sW, p.w_tile_bytes);
+            tma_load_4d(&tmap, &sync->full[stage], sX, cib * p.tile_ci,
+                        c.ox0 * p.stride + (kx - half) * p.dil, c.oy0 * p.stride + (ky - half) * p.dil,
+                        c.n);
+          }
+          __syncwarp();
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (warp-uniform loop)
+    {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       const int ksteps = (int)(p.pitch / 32u);  // UMMA K = 16 elements = 32 bytes
+      const uint64_t d_hi = umma_smem_desc(0u, p.pitch);
+      const uint32_t wstage16 = p.w_stage_bytes >> 4;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile(p, t);
         if (c.je == c.jb) continue;  // nothing live: the epilogue does not touch TMEM either
@@ -155,26 +161,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         for (int j = c.jb; j < c.je; ++j) {
           mbar_wait(&sync->full[stage], phase);
           tc_fence_after();
-          const uint32_t sW = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sX = sW + p.w_stage_bytes;
-          const uint64_t dW = umma_smem_desc(sW, p.pitch);
-          const uint64_t dX = umma_smem_desc(sX, p.pitch);
-          for (int i = 0; i < ksteps; ++i) {
-            const uint32_t accum = (j > c.jb || i > 0) ? 1u : 0u;
-            if (MODE != MODE_P)
-              umma_f16(d_tmem, dW + (uint64_t)(2 * i), dX + (uint64_t)(2 * i), p.idesc, accum);
-            else
-              umma_f16(d_tmem, dX + (uint64_t)(2 * i), dW + (uint64_t)(2 * i), p.idesc, accum);
+          const uint32_t sW16 = smem_u32(smem + (size_t)stage * p.stage_bytes) >> 4;
+          const uint32_t sX16 = sW16 + wstage16;
+          if (elect_one()) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (i < ksteps) {
+                const uint32_t accum = (j > c.jb || i > 0) ? 1u : 0u;
+                const uint64_t dW = d_hi | (uint64_t)(sW16 + 2u * i), dX = d_hi | (uint64_t)(sX16 + 2u * i);
+                if (MODE != MODE_P) umma_f16(d_tmem, dW, dX, p.idesc, accum);
+                else umma_f16(d_tmem, dX, dW, p.idesc, accum);
+              }
+            }
+            umma_commit(&sync->empty[stage]);  // smem slot free once these MMAs retire
           }
-          umma_commit(&sync->empty[stage]);  // smem slot free once these MMAs retire
+          __syncwarp();
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&sync->tfull[acc]);      // accumulator complete
+        if (elect_one()) umma_commit(&sync->tfull[acc]);      // accumulator complete
+        __syncwarp();
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-    __syncwarp();
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may read
