@@ -443,6 +443,7 @@ using namespace drnb200;
 
 struct drnb200_stem_plan {
   drnb200::GMapCache cache;
+  drnb200::StemTxState* tx;      // Toeplitz-weight kernel (default); null -> im2col-gather kernel
   int N, H, W, act_dtype;
   float *d_wpad, *d_scale, *d_shift;
   int32_t *d_row_ptr, *d_kblk;
@@ -453,6 +454,7 @@ extern "C" void drnb200_stem_plan_destroy(drnb200_stem_plan* p) {
   if (!p) return;
   cudaFree(p->d_wpad); cudaFree(p->d_scale); cudaFree(p->d_shift);
   cudaFree(p->d_row_ptr); cudaFree(p->d_kblk); cudaFree(p->d_wpacked);
+  stem_tx_destroy(p->tx);
   delete p;
 }
 
@@ -481,6 +483,9 @@ extern "C" int drnb200_stem_plan_create(drnb200_stem_plan** out, const float* w_
   stem_pad_kernel<<<(16 * 160 + 255) / 256, 256, 0, st>>>(w_oihw, p->d_wpad, p->d_row_ptr, p->d_kblk);
   int rc = drnb200_pack_weights(p->d_wpad, nullptr, 16, 160, 1, 1, 16, 16, p->d_row_ptr, p->d_kblk,
                                 act_dtype, p->d_wpacked, stream);
+  static const char* env = getenv("DRNB200_STEM");      // A/B knob: "gather" keeps the im2col-gather stem
+  p->tx = nullptr;
+  if (rc == DRNB200_OK && !(env && env[0] == 'g')) rc = stem_tx_create(&p->tx, w_oihw, act_dtype, st);
   if (rc == DRNB200_OK) {
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize(stem plan)");
@@ -493,6 +498,9 @@ extern "C" int drnb200_stem_plan_create(drnb200_stem_plan** out, const float* w_
 extern "C" int drnb200_stem_plan_forward(drnb200_stem_plan* plan, const float* x_nchw, void* y_nhwc,
                                          void* stream) {
   DRN_REQUIRE(plan && x_nchw && y_nhwc, "stem_plan_forward: null pointer");
+  if (plan->tx)
+    return stem_tx_forward(plan->tx, x_nchw, y_nhwc, plan->d_scale, plan->d_shift, plan->N, plan->H, plan->W,
+                           plan->act_dtype, (cudaStream_t)stream);
   GatherParams p{};
   p.x = x_nchw; p.y = y_nhwc; p.w_packed = reinterpret_cast<const uint8_t*>(plan->d_wpacked);
   p.kblk = plan->d_kblk; p.scale = plan->d_scale; p.shift = plan->d_shift; p.n_kb = G_MAX_KB;

@@ -62,4 +62,10 @@ constexpr int TC_MODE_GATHER = 3;
 bool conv_halo_supported(const drnb200_conv_desc& d);       // stride-1 3x3, Cin,Cout <= 64 (conv_halo.cu)
 int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st);
 constexpr int TC_MODE_HALO = 4;
+// Toeplitz-weight stem (stem_tx.cu)
+struct StemTxState;
+int stem_tx_create(StemTxState** out, const float* w_oihw, int act_dtype, cudaStream_t st);
+void stem_tx_destroy(StemTxState* s);
+int stem_tx_forward(StemTxState* s, const float* x, void* y, const float* scale, const float* shift, int N,
+                    int H, int W, int act_dtype, cudaStream_t st);
 }  // namespace drnb200
