@@ -394,6 +394,10 @@ static const ConvCase kCases[] = {
     {"L4_res",             8,128,256, 128,128, 3, 1, 1, 1, 1, 1, 0, 128, 64, 2, 0.5f, 0, 0, 1},
     {"L4_s2",              8,256,512, 64, 128, 3, 2, 1, 1, 0, 1, 0, 128, 64, 2, 1.0f, 0, 0, 1},
     {"L3_res",             8,256,512, 64,  64, 3, 1, 1, 1, 1, 1, 0,  64, 64, 2, 1.0f, 0, 0, 1},
+    {"L3_c1",              8,512,1024, 32,  64, 3, 2, 1, 1, 0, 1, 0,  64, 32, 2, 1.0f, 0, 0, 1},
+    {"L3_ds",              8,512,1024, 32,  64, 1, 2, 1, 0, 0, 1, 0,  64, 32, 2, 1.0f, 0, 0, 1},
+    {"L6_ds",              8,128,256, 256,512, 1, 1, 1, 0, 0, 1, 0, 128, 64, 2, 0.25f,0, 0, 1},
+    {"L5_c1",              8,128,256, 128,256, 3, 1, 2, 1, 0, 1, 0, 128, 64, 2, 0.5f, 0, 0, 1},
     {"L2",                 8,1024,2048,16, 32, 3, 2, 1, 1, 0, 1, 0,  32, 16, 2, 1.0f, 0, 0, 1},
     {"L1",                 8,1024,2048,16, 16, 3, 1, 1, 1, 0, 1, 0,  16, 16, 2, 1.0f, 0, 0, 1},
 };

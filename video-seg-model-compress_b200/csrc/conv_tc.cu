@@ -38,7 +38,9 @@ constexpr int kEpRing = 4;     // staging buffers of the MODE_T epilogue
 constexpr int kEpChunkPx = 32; // pixels per staged chunk (one tcgen05.ld.32x32b.x32 per warp)
 constexpr int kEpBufBytes = kEpChunkPx * 256;
 
-struct __align__(8) TcSync {
+struct __align__(16) TcSync {
+  alignas(16) float scale[256];   // MODE_P: BN affine of all (<= 256) output channels, read by every pixel thread
+  alignas(16) float shift[256];   //         (no L1 is left once the CTA takes ~all shared memory)
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tfull[2];
@@ -108,6 +110,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   if (warp == 1) {
     tmem_alloc(&sync->tmem_base, kTmemCols);
     tmem_relinquish();
+  }
+  if (MODE == MODE_P) {
+    for (int ch = threadIdx.x; ch < 256; ch += kTcThreads) {
+      sync->scale[ch] = ch < p.Cout ? __ldg(p.scale + ch) : 0.f;
+      sync->shift[ch] = ch < p.Cout ? __ldg(p.shift + ch) : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -346,8 +354,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             float o[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              o[i] = finish<DT>(__uint_as_float(v[i]), __ldg(p.scale + cb + i),
-                                __ldg(p.shift + cb + i), r[i], p.relu);
+              o[i] = finish<DT>(__uint_as_float(v[i]), sync->scale[cb + i], sync->shift[cb + i], r[i], p.relu);
             if (p.out_f32) {
               float4* yp = reinterpret_cast<float4*>(y32 + off0 + cb);
 #pragma unroll
