@@ -105,8 +105,12 @@ int  drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_conv_desc* 
                               const float* bn_scale, const float* bn_shift);
 int  drnb200_conv_forward(drnb200_conv_plan* plan, const void* x_nhwc, const void* residual_or_null,
                           void* y_nhwc, void* stream);
-/* what the plan resolved to: 1 = direct, 2 = tcgen05; number of kernel launches per forward */
+/* what the plan resolved to: 1 = direct (CUDA cores), 2 = tcgen05 */
 int  drnb200_conv_plan_impl(const drnb200_conv_plan* plan);
+/* which tcgen05 kernel: 0 = conv_tc MODE_T (128-cout tiles, staged epilogue), 1 = conv_tc MODE_P (pixels as M),
+ * 2 = conv_tc MODE_T with float32 output, 3 = conv_gather (im2col in smem), 4 = conv_halo (shifted windows);
+ * -1 for direct plans */
+int  drnb200_conv_plan_mode(const drnb200_conv_plan* plan);
 /* live multiply-accumulates of one forward (tile-list granularity) — the numerator of tensor-pipe
  * utilisation counted at block granularity; element-granularity MACs are computed by the host. */
 int64_t drnb200_conv_plan_tile_macs(const drnb200_conv_plan* plan);

@@ -28,7 +28,7 @@
 
 namespace drnb200 {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 352;   // TMA, MMA, 2 x 4 epilogue warps, epilogue-TMA warp (MODE_T); MODE_P uses warps 0-5
 constexpr int kMaxStages = 8;
 constexpr int MODE_T = 0;      // staged epilogue (16-bit output)
 constexpr int MODE_P = 1;
@@ -45,7 +45,9 @@ struct __align__(16) TcSync {
   uint64_t empty[kMaxStages];
   uint64_t tfull[2];
   uint64_t tempty[2];
-  uint64_t rfull[kEpRing];
+  uint64_t rfull[kEpRing];    // staged epilogue: residual chunk landed in ring slot (TMA)
+  uint64_t sfree[kEpRing];    //                  ring slot may be overwritten (no-residual layers)
+  uint64_t sdone[kEpRing];    //                  the owning epilogue group finished the chunk
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -96,14 +98,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       tma_prefetch_desc(&tmap_y);
       if (p.has_res) tma_prefetch_desc(&tmap_r);
     }
-    for (int b = 0; b < kEpRing; ++b) mbar_init(&sync->rfull[b], 1);
+    for (int b = 0; b < kEpRing; ++b) {
+      mbar_init(&sync->rfull[b], 1);
+      mbar_init(&sync->sfree[b], 1);
+      mbar_init(&sync->sdone[b], 4);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&sync->full[s], 1);
       mbar_init(&sync->empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sync->tfull[a], 1);
-      mbar_init(&sync->tempty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&sync->tempty[a], MODE == MODE_T ? 8 : 4);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -202,89 +208,138 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
     if (MODE == MODE_T) {
       // ------------------------------------------------ staged: smem transpose + TMA load/store
-      const bool leader = (warp == 2 && lane == 0);       // issues every TMA of the epilogue
-      const int cl = q * 32 + lane;                       // cout inside the 128-cout tile
-      const int nch = p.ep_nch;
-      uint32_t k = 0;                                     // flat chunk counter (ring position)
-      auto chunk_xy = [&](const TileCoord& c, int qq, int& cx, int& cy) {
-        const int j0 = qq * kEpChunkPx;
-        cx = c.ox0 + (j0 & (p.TW - 1));
-        cy = c.oy0 + (j0 >> p.tw_shift);
-      };
-      if (leader && p.has_res && (int)blockIdx.x < p.total_tiles) {   // residual of the very first chunk
-        const TileCoord c0 = decode_tile(p, blockIdx.x);
-        int cx, cy;
-        chunk_xy(c0, 0, cx, cy);
-        mbar_arrive_expect_tx(&sync->rfull[0], kEpBufBytes);
-        tma_load_4d(&tmap_r, &sync->rfull[0], stg, c0.ot * 128, cx, cy, c0.n);
-      }
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile(p, t);
-        const bool live = c.je > c.jb;
-        const int co = c.ot * 128 + cl;
-        const float sc = __ldg(p.scale + co), sh = __ldg(p.shift + co);
-        if (live) {
-          mbar_wait(&sync->tfull[acc], acc_phase);
-          tc_fence_after();
-        }
-        const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-        for (int qq = 0; qq < nch; ++qq, ++k) {
-          const uint32_t b = k & (kEpRing - 1);
-          uint8_t* buf = stg + b * kEpBufBytes;
-          if (leader) {
-            // stores k-1 and k-2 may still be reading their buffers; k-3 (the previous user of ring
-            // slot (k+1)%4) is done, so the next chunk's residual can land there
-            bulk_wait_group_read<2>();
-            if (p.has_res) {
-              int nt = t, nq = qq + 1;
-              if (nq == nch) { nq = 0; nt = t + gridDim.x; }
-              if (nt < p.total_tiles) {
-                const TileCoord cn = (nt == t) ? c : decode_tile(p, nt);
-                int cx, cy;
-                chunk_xy(cn, nq, cx, cy);
-                const uint32_t nb = (k + 1) & (kEpRing - 1);
-                mbar_arrive_expect_tx(&sync->rfull[nb], kEpBufBytes);
-                tma_load_4d(&tmap_r, &sync->rfull[nb], stg + nb * kEpBufBytes, cn.ot * 128, cx, cy, cn.n);
+      // warps 2-9 = two groups of four warps taking alternate 32-pixel chunks (flat chunk index k: group k&1,
+      // ring slot k&3); warp 10 issues every residual load and output store and recycles the ring slots.
+      if (warp == 10) {
+        // ---- epilogue TMA warp (warp-uniform loop; one elected lane issues and owns the bulk groups)
+        const int nch = p.ep_nch;
+        auto chunk_xy = [&](const TileCoord& c, int qq, int& cx, int& cy) {
+          const int j0 = qq * kEpChunkPx;
+          cx = c.ox0 + (j0 & (p.TW - 1));
+          cy = c.oy0 + (j0 >> p.tw_shift);
+        };
+        constexpr int D = 2;                       // loads run D chunks ahead of stores
+        int hist_ot[D], hist_cx[D], hist_cy[D], hist_n[D];
+        uint32_t k = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+          const TileCoord c = decode_tile(p, t);
+          for (int qq = 0; qq < nch; ++qq, ++k) {
+            const uint32_t b = k & (kEpRing - 1);
+            int cx, cy;
+            chunk_xy(c, qq, cx, cy);
+            if (k >= (uint32_t)D) {                // finish chunk k-D: its group is done -> store it
+              const uint32_t kb = k - D, bb = kb & (kEpRing - 1);
+              mbar_wait(&sync->sdone[bb], (kb / kEpRing) & 1u);
+              if (elect_one()) {
+                tma_store_4d(&tmap_y, stg + bb * kEpBufBytes, hist_ot[kb % D] * 128, hist_cx[kb % D],
+                             hist_cy[kb % D], hist_n[kb % D]);
+                bulk_commit_group();
               }
+              __syncwarp();
+            }
+            // prepare chunk k: ring slot b was last used by chunk k-4, whose store has been issued
+            // (k-4 <= k-1-D) and is complete once at most one newer store is still reading
+            if (elect_one()) {
+              bulk_wait_group_read<1>();
+              mbar_arrive(&sync->sfree[b]);
+            }
+            __syncwarp();
+            hist_ot[k % D] = c.ot; hist_cx[k % D] = cx; hist_cy[k % D] = cy; hist_n[k % D] = c.n;
+          }
+        }
+        // drain: the last min(k, D) chunks still have to be stored
+        for (uint32_t kb = (k >= (uint32_t)D ? k - D : 0u); kb < k; ++kb) {
+          const uint32_t bb = kb & (kEpRing - 1);
+          mbar_wait(&sync->sdone[bb], (kb / kEpRing) & 1u);
+          if (elect_one()) {
+            tma_store_4d(&tmap_y, stg + bb * kEpBufBytes, hist_ot[kb % D] * 128, hist_cx[kb % D], hist_cy[kb % D],
+                         hist_n[kb % D]);
+            bulk_commit_group();
+          }
+          __syncwarp();
+        }
+        if (elect_one()) bulk_wait_group<0>();     // all stores complete before the CTA retires
+        __syncwarp();
+      } else {
+        // ---- epilogue groups
+        const int grp = (warp - 2) >> 2;
+        const int cl = q * 32 + lane;              // cout inside the 128-cout tile
+        const int nch = p.ep_nch;
+        uint32_t k0 = 0;                           // flat chunk index of the tile's first chunk
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+          const TileCoord c = decode_tile(p, t);
+          const bool live = c.je > c.jb;
+          const int co = c.ot * 128 + cl;
+          const float sc = __ldg(p.scale + co), sh = __ldg(p.shift + co);
+          // residual chunk [32 px][128 couts] = 8 KB: four coalesced 16-byte loads per thread (two 256-byte
+          // pixel rows per warp instruction), issued one chunk ahead; they are parked in the ring slot and
+          // then read back transposed (thread = cout) exactly like the TMA-delivered residual used to be
+          const int tig = (warp - 2 - 4 * grp) * 32 + lane;      // thread index inside the group (0..127)
+          auto load_res = [&](int qq, uint4 (&r)[4]) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = u * 128 + tig, i = idx >> 4, part = idx & 15;
+              const int j = qq * kEpChunkPx + i;
+              const int oy = c.oy0 + (j >> p.tw_shift), ox = c.ox0 + (j & (p.TW - 1));
+              r[u] = make_uint4(0u, 0u, 0u, 0u);
+              if (oy < p.OH && ox < p.OW)
+                r[u] = __ldg(reinterpret_cast<const uint4*>(
+                    res16 + (((size_t)c.n * p.OH + oy) * p.OW + ox) * p.Cout + c.ot * 128 + part * 8));
+            }
+          };
+          int qq = (int)((k0 ^ (uint32_t)grp) & 1u);       // first chunk of this tile owned by this group
+          uint4 rcur[4], rnext[4];
+          if (p.has_res && qq < nch) load_res(qq, rcur);
+          if (live) {
+            mbar_wait(&sync->tfull[acc], acc_phase);
+            tc_fence_after();
+          }
+          const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
+          for (; qq < nch; qq += 2) {
+            const uint32_t k = k0 + (uint32_t)qq;
+            const uint32_t b = k & (kEpRing - 1);
+            uint8_t* buf = stg + b * kEpBufBytes;
+            if (p.has_res && qq + 2 < nch) load_res(qq + 2, rnext);
+            mbar_wait(&sync->sfree[b], (k / kEpRing) & 1u);   // the slot's previous store has drained
+            if (p.has_res) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(buf + (u * 128 + tig) * 16) = rcur[u];
+              named_bar_sync(1 + grp, 128);           // the whole residual chunk is in the slot
+            }
+            uint32_t v[32];
+            if (live) {
+              tmem_ld32(t_addr + (uint32_t)(qq * kEpChunkPx), v);
+              tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0u;
+            }
+            uint16_t* col = reinterpret_cast<uint16_t*>(buf) + cl;   // [pixel][128 couts]
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float r = p.has_res ? Act<DT>::to_f32(col[i * 128]) : 0.f;
+              col[i * 128] = Act<DT>::from_f32(finish<DT>(__uint_as_float(v[i]), sc, sh, r, p.relu));
+            }
+            fence_proxy_async_smem();              // st.shared -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sync->sdone[b]);
+            if (p.has_res) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) rcur[u] = rnext[u];
             }
           }
-          named_bar_sync(1, 128);                          // ring slot b is free for this chunk
-          if (p.has_res) mbar_wait(&sync->rfull[b], (k / kEpRing) & 1u);
-          uint32_t v[32];
-          if (live) {
-            tmem_ld32(t_addr + (uint32_t)(qq * kEpChunkPx), v);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0u;
-          }
-          uint16_t* col = reinterpret_cast<uint16_t*>(buf) + cl;   // [pixel][128 couts]
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float r = p.has_res ? Act<DT>::to_f32(col[i * 128]) : 0.f;
-            col[i * 128] = Act<DT>::from_f32(finish<DT>(__uint_as_float(v[i]), sc, sh, r, p.relu));
-          }
-          if (live && qq == nch - 1) {                     // accumulator fully read: hand it back
+          k0 += (uint32_t)nch;
+          if (live) {                              // this warp has read all of its chunks of the accumulator
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sync->tempty[acc]);
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
           }
-          fence_proxy_async_smem();                        // st.shared -> visible to the TMA store
-          named_bar_sync(2, 128);
-          if (leader) {
-            int cx, cy;
-            chunk_xy(c, qq, cx, cy);
-            tma_store_4d(&tmap_y, buf, c.ot * 128, cx, cy, c.n);
-            bulk_commit_group();
-          }
-        }
-        if (live) {
-          acc ^= 1u;
-          if (acc == 0) acc_phase ^= 1u;
         }
       }
-      if (leader) bulk_wait_group<0>();                    // all stores complete before the CTA retires
-    } else {
+    } else if (warp < 6) {
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord c = decode_tile(p, t);
       const bool live = c.je > c.jb;

@@ -37,6 +37,7 @@ SIGNATURES = {
     "drnb200_conv_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
     "drnb200_conv_forward": (C.c_int, [_P, _P, _P, _P, _P]),
     "drnb200_conv_plan_impl": (C.c_int, [_P]),
+    "drnb200_conv_plan_mode": (C.c_int, [_P]),
     "drnb200_conv_plan_tile_macs": (C.c_int64, [_P]),
     "drnb200_conv_plan_destroy": (None, [_P]),
     "drnb200_stem_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
