@@ -295,7 +295,7 @@ def main():
             shapes[i] = (oh, ow)
             macs = B * oh * ow * op.live_elems
             c = op.conv
-            io_bytes = 2 * B * (shapes[src][0] * shapes[src][1] * c.in_channels + oh * ow * c.out_channels)
+            io_bytes = 2 * B * (shapes[src][0] * shapes[src][1] * c.in_channels + oh * ow * op.out_channels)
             lms = per_layer[op.key]
             mode = max([lib.drnb200_conv_plan_mode(pl) for pl in op.plans.values()] or [-1])
             layers.append({"layer": op.key, "ms": lms, "live_gmac": macs / 1e9, "kernel": KERNELS.get(mode, "?"),

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRNB200_VERSION 100
+#define DRNB200_VERSION 101
 
 /* error codes */
 #define DRNB200_OK          0
@@ -96,6 +96,14 @@ typedef struct drnb200_conv_desc {
   int32_t out_f32;          /* write y as float32 NHWC instead of act_dtype (hand-off to the head) */
   int32_t tile_o, tile_ci;  /* granularity the tile list / packed weights were built with        */
   int32_t impl;             /* DRNB200_IMPL_*                                                    */
+  /* channel sub-ranges of wider NHWC tensors (0 = tightly packed).  They let one launch compute a residual
+   * block's conv1 AND its 1x1 downsample as [conv1 | downsample] output channels (the downsample is the centre tap
+   * of a 3x3 with the same stride; its other taps are dead K-blocks the tile list skips), and let conv2 then read
+   * its input and its residual from the two halves of that tensor (drn.py:49-65, :181-186). */
+  int32_t x_cpitch;         /* channels per pixel of the tensor x lives in (>= Cin); x uses channels [0, Cin) */
+  int32_t res_cpitch;       /* channels per pixel of the tensor the residual lives in (>= Cout)              */
+  int32_t res_coffset;      /* first channel of the residual inside that tensor                              */
+  int32_t relu_n;           /* apply ReLU only to output channels < relu_n (0 = use `relu` for all channels) */
 } drnb200_conv_desc;
 
 typedef struct drnb200_conv_plan drnb200_conv_plan;

@@ -64,8 +64,10 @@ def test_engine_graph_matches_module_tree():
         m = drnb200.DRNSeg(arch, 19, pretrained=False)
         eng = m.engine()
         convs = [k for k, s in load_keys(arch).items() if len(s) == 4 and s[2] in (1, 3) and k.startswith("layer.")]
-        assert sorted(op.key + ".weight" for op in eng.ops) == sorted(convs)
-        assert len(eng.ops) == n_convs
+        assert sorted(k + ".weight" for op in eng.ops for k in op.keys) == sorted(convs)
+        assert sum(len(op.keys) for op in eng.ops) == n_convs
+        unfused = drnb200.engine.Engine(m, fuse_downsample=False)
+        assert len(unfused.ops) == n_convs and len(eng.ops) <= n_convs
         for i, op in enumerate(eng.ops):
             assert op.input_from is None or op.input_from < i
             assert op.residual_from is None or op.residual_from < i
@@ -227,7 +229,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), name
     lib = ffi.lib()
-    assert lib.drnb200_version() == 100
+    assert lib.drnb200_version() == 101
     # argument validation happens before any CUDA call, so it is testable here
     assert lib.drnb200_compact_mask(None, 8, 8, 3, 3, 8, 8, None, None, None, None) == -1
     assert b"null pointer" in lib.drnb200_last_error()

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const ConvParams p) {
     const int iy = oy * p.stride + (ky - half) * p.dil;
     const int ix = ox * p.stride + (kx - half) * p.dil;
     if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) continue;  // zero padding
-    const uint16_t* xp = x + (((size_t)n * p.H + iy) * p.W + ix) * p.Cin + (size_t)cib * p.tile_ci;
+    const uint16_t* xp = x + (((size_t)n * p.H + iy) * p.W + ix) * p.x_cpitch + (size_t)cib * p.tile_ci;
     const uint8_t* tile = p.w_packed + (size_t)j * tile_bytes;
     for (int k8 = 0; k8 < p.tile_ci / 8; ++k8) {
       const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xp) + k8);
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const ConvParams p) {
   for (int r = 0; r < 8; ++r) out[r] = fmaf(acc[r], __ldg(p.scale + c0 + r), __ldg(p.shift + c0 + r));
   if (p.has_res) {
     const uint4 rv = __ldg(reinterpret_cast<const uint4*>(
-        reinterpret_cast<const uint16_t*>(p.residual) + off));
+        reinterpret_cast<const uint16_t*>(p.residual) + (size_t)pix * p.res_pitch + p.res_coff + c0));
     const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -73,10 +73,9 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const ConvParams p) {
       out[2 * q + 1] += Act<DT>::to_f32((uint16_t)(rw[q] >> 16));
     }
   }
-  if (p.relu) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) out[r] = fmaxf(out[r], 0.f);
-  }
+  for (int r = 0; r < 8; ++r)
+    if (c0 + r < p.relu_n) out[r] = fmaxf(out[r], 0.f);
   if (p.out_f32) {
     float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + off);
     yp[0] = make_float4(out[0], out[1], out[2], out[3]);

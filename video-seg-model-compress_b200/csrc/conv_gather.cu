@@ -406,7 +406,7 @@ bool conv_gather_supported(const drnb200_conv_desc& d) {
   if (env && env[0] == '0') return false;
   return d.ksize == 3 && d.Cin == 16 && d.tile_ci == 16 && d.tile_o == d.Cout &&
          (d.Cout == 16 || d.Cout == 32) && d.dilation == 1 && (d.stride == 1 || d.stride == 2) &&
-         !d.has_residual && !d.out_f32;
+         !d.has_residual && !d.out_f32 && (d.x_cpitch == 0 || d.x_cpitch == d.Cin) && d.relu_n == 0;
 }
 
 int conv_gather_launch(drnb200_conv_plan* plan, cudaStream_t st) {

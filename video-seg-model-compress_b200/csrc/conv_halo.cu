@@ -43,7 +43,7 @@ struct HaloParams {
   const int32_t* kblk;       // live taps
   const float* scale;
   const float* shift;
-  int n_kb, N, H, W, Cin, Cout, dil, relu, has_res;
+  int n_kb, N, H, W, Cin, Cout, dil, relu_n, has_res, x_cpitch, res_pitch, res_coff;
   int tiles_x, tiles_y, total_tiles, halo_h, ring;
   uint32_t magic_x, magic_y;   // ceil(2^32 / tiles_{x,y}): exact quotients by __umulhi for t < 2^32 / divisor
   uint32_t pitch, halo_bytes, w_tile_bytes, idesc, base_off_mode;
@@ -200,14 +200,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
       const HTile c = h_decode(p, t);
       const int ox = c.ox0 + (m & (H_TW - 1)), oy = c.oy0 + (m >> 3);
       const bool valid = ox < p.W && oy < p.H;
-      const size_t off0 = (((size_t)c.n * p.H + oy) * p.W + ox) * p.Cout;
+      const size_t pix0 = ((size_t)c.n * p.H + oy) * p.W + ox;
+      const size_t off0 = pix0 * p.Cout;
       // the residual of this pixel (<= 128 B) is requested before the accumulator wait so that its
       // latency overlaps the MMAs instead of serialising behind every 16-channel group
       uint4 rv[8];
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         rv[g] = make_uint4(0u, 0u, 0u, 0u);
-        if (p.has_res && valid && g * 8 < p.Cout) rv[g] = __ldg(reinterpret_cast<const uint4*>(res16 + off0) + g);
+        if (p.has_res && valid && g * 8 < p.Cout)
+          rv[g] = __ldg(reinterpret_cast<const uint4*>(res16 + pix0 * p.res_pitch + p.res_coff) + g);
       }
       mbar_wait(&sync->t_full[acc], (uint32_t)(i / H_ACC) & 1u);
       tc_fence_after();
@@ -235,7 +237,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
                           Act<DT>::to_f32((uint16_t)(rw[e] & 0xFFFFu));
                 float d = fmaf(__uint_as_float(v[2 * e + 1]), scv[2 * h2 + 1], shv[2 * h2 + 1]) +
                           Act<DT>::to_f32((uint16_t)(rw[e] >> 16));
-                if (p.relu) { a = fmaxf(a, 0.f); d = fmaxf(d, 0.f); }
+                if (cb + 2 * e < p.relu_n) a = fmaxf(a, 0.f);
+                if (cb + 2 * e + 1 < p.relu_n) d = fmaxf(d, 0.f);
                 w[e] = (uint32_t)Act<DT>::from_f32(a) | ((uint32_t)Act<DT>::from_f32(d) << 16);
               }
             }
@@ -295,8 +298,8 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   p.scale = c.scale; p.shift = c.shift;
   p.n_kb = plan->h_row_ptr[1];
   if (p.n_kb == 0) return conv_direct_launch(plan, st);   // everything pruned: y = act(shift + res)
-  p.N = c.N; p.H = c.H; p.W = c.W; p.Cin = c.Cin; p.Cout = c.Cout; p.dil = c.dil; p.relu = c.relu;
-  p.has_res = c.has_res;
+  p.N = c.N; p.H = c.H; p.W = c.W; p.Cin = c.Cin; p.Cout = c.Cout; p.dil = c.dil; p.relu_n = c.relu_n;
+  p.has_res = c.has_res; p.x_cpitch = c.x_cpitch; p.res_pitch = c.res_pitch; p.res_coff = c.res_coff;
   p.pitch = (uint32_t)c.Cin * 2u;
   p.halo_h = H_TH + 2 * c.dil;
   p.halo_bytes = (uint32_t)p.halo_h * H_WP * p.pitch;
@@ -328,7 +331,8 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
     auto fn = h_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return DRNB200_E_CUDA; }
     cuuint64_t gdim[4] = {(cuuint64_t)c.Cin, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
-    cuuint64_t gstr[3] = {(cuuint64_t)c.Cin * 2, (cuuint64_t)c.W * c.Cin * 2, (cuuint64_t)c.H * c.W * c.Cin * 2};
+    cuuint64_t gstr[3] = {(cuuint64_t)c.x_cpitch * 2, (cuuint64_t)c.W * c.x_cpitch * 2,
+                          (cuuint64_t)c.H * c.W * c.x_cpitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)c.Cin, (cuuint32_t)H_WP, (cuuint32_t)p.halo_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMapSwizzle sw = p.pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B

@@ -20,6 +20,9 @@ struct ConvParams {
   int taps, stride, dil;
   int tile_o, tile_ci, n_ot, n_cib;
   int relu, has_res, out_f32;
+  int x_cpitch;             // channels per pixel of the tensor x lives in
+  int res_pitch, res_coff;  // residual: channels per pixel of its tensor, first channel
+  int relu_n;               // ReLU applies to output channels < relu_n (Cout: all, 0: none)
   // ---- tcgen05 path only
   const int32_t* ot_order;  // output tiles sorted by decreasing live count
   int TW, TH, tw_shift;     // pixel tile (powers of two), NT = TW*TH

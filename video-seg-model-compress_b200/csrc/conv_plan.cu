@@ -43,6 +43,17 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
   p.tile_o = d.tile_o; p.tile_ci = d.tile_ci;
   p.n_ot = d.Cout / d.tile_o; p.n_cib = d.Cin / d.tile_ci;
   p.relu = d.relu; p.has_res = d.has_residual; p.out_f32 = d.out_f32;
+  p.x_cpitch = d.x_cpitch > 0 ? d.x_cpitch : d.Cin;
+  p.res_pitch = d.res_cpitch > 0 ? d.res_cpitch : d.Cout;
+  p.res_coff = d.res_coffset;
+  p.relu_n = d.relu_n > 0 ? d.relu_n : (d.relu ? d.Cout : 0);
+  if (p.x_cpitch < d.Cin || p.x_cpitch % 8 || p.res_pitch % 8 || p.res_coff % 8 || p.res_coff < 0 ||
+      p.res_coff + d.Cout > p.res_pitch || p.relu_n > d.Cout) {
+    set_error("conv_plan_create: bad channel sub-range (x_cpitch=%d res_cpitch=%d res_coffset=%d relu_n=%d)",
+              d.x_cpitch, d.res_cpitch, d.res_coffset, d.relu_n);
+    delete plan;
+    return DRNB200_E_ARG;
+  }
 
   plan->h_row_ptr.resize(p.n_ot + 1);
   cudaError_t e = cudaMemcpy(plan->h_row_ptr.data(), row_ptr, sizeof(int32_t) * (p.n_ot + 1),

@@ -271,6 +271,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           const bool live = c.je > c.jb;
           const int co = c.ot * 128 + cl;
           const float sc = __ldg(p.scale + co), sh = __ldg(p.shift + co);
+          const int relu = co < p.relu_n;
           // residual chunk [32 px][128 couts] = 8 KB: four coalesced 16-byte loads per thread (two 256-byte
           // pixel rows per warp instruction), issued one chunk ahead; they are parked in the ring slot and
           // then read back transposed (thread = cout) exactly like the TMA-delivered residual used to be
@@ -284,7 +285,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               r[u] = make_uint4(0u, 0u, 0u, 0u);
               if (oy < p.OH && ox < p.OW)
                 r[u] = __ldg(reinterpret_cast<const uint4*>(
-                    res16 + (((size_t)c.n * p.OH + oy) * p.OW + ox) * p.Cout + c.ot * 128 + part * 8));
+                    res16 + (((size_t)c.n * p.OH + oy) * p.OW + ox) * p.res_pitch + p.res_coff + c.ot * 128 +
+                    part * 8));
             }
           };
           int qq = (int)((k0 ^ (uint32_t)grp) & 1u);       // first chunk of this tile owned by this group
@@ -319,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float r = p.has_res ? Act<DT>::to_f32(col[i * 128]) : 0.f;
-              col[i * 128] = Act<DT>::from_f32(finish<DT>(__uint_as_float(v[i]), sc, sh, r, p.relu));
+              col[i * 128] = Act<DT>::from_f32(finish<DT>(__uint_as_float(v[i]), sc, sh, r, relu));
             }
             fence_proxy_async_smem();              // st.shared -> visible to the TMA store
             __syncwarp();
@@ -368,9 +370,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             const int j = ch + i;
             const int oy = c.oy0 + (j >> p.tw_shift), ox = c.ox0 + (j & (p.TW - 1));
             if (oy < p.OH && ox < p.OW) {
-              const size_t off = (((size_t)c.n * p.OH + oy) * p.OW + ox) * p.Cout + co;
-              const float r = p.has_res ? Act<DT>::to_f32(__ldg(res16 + off)) : 0.f;
-              const float o = finish<DT>(__uint_as_float(v[i]), sc, sh, r, p.relu);
+              const size_t pix = ((size_t)c.n * p.OH + oy) * p.OW + ox;
+              const size_t off = pix * p.Cout + co;
+              const float r = p.has_res ? Act<DT>::to_f32(__ldg(res16 + pix * p.res_pitch + p.res_coff + co)) : 0.f;
+              const float o = finish<DT>(__uint_as_float(v[i]), sc, sh, r, co < p.relu_n);
               if (p.out_f32) y32[off] = o;
               else y16[off] = Act<DT>::from_f32(o);
             }
@@ -381,7 +384,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const int j = q * 32 + lane;
         const int oy = c.oy0 + (j >> p.tw_shift), ox = c.ox0 + (j & (p.TW - 1));
         const bool valid = (oy < p.OH) && (ox < p.OW);
-        const size_t off0 = (((size_t)c.n * p.OH + oy) * p.OW + ox) * p.Cout;
+        const size_t pix0 = ((size_t)c.n * p.OH + oy) * p.OW + ox;
+        const size_t off0 = pix0 * p.Cout;
         for (int cb = 0; cb < p.Cout; cb += 16) {
           uint32_t v[16];
           if (live) {
@@ -394,7 +398,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           if (valid) {
             float r[16];
             if (p.has_res) {
-              const uint4* rp = reinterpret_cast<const uint4*>(res16 + off0 + cb);
+              const uint4* rp = reinterpret_cast<const uint4*>(res16 + pix0 * p.res_pitch + p.res_coff + cb);
               const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
               const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -409,7 +413,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             float o[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              o[i] = finish<DT>(__uint_as_float(v[i]), sync->scale[cb + i], sync->shift[cb + i], r[i], p.relu);
+              o[i] = finish<DT>(__uint_as_float(v[i]), sync->scale[cb + i], sync->shift[cb + i], r[i],
+                                cb + i < p.relu_n);
             if (p.out_f32) {
               float4* yp = reinterpret_cast<float4*>(y32 + off0 + cb);
 #pragma unroll
@@ -601,8 +606,8 @@ static int encode_tmap(drnb200_conv_plan* plan, const void* x) {
     return DRNB200_E_CUDA;
   }
   cuuint64_t gdim[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
-  cuuint64_t gstr[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.W * p.Cin * 2,
-                        (cuuint64_t)p.H * p.W * p.Cin * 2};
+  cuuint64_t gstr[3] = {(cuuint64_t)p.x_cpitch * 2, (cuuint64_t)p.W * p.x_cpitch * 2,
+                        (cuuint64_t)p.H * p.W * p.x_cpitch * 2};
   cuuint32_t box[4] = {(cuuint32_t)p.tile_ci, (cuuint32_t)(p.TW * d.stride),
                        (cuuint32_t)(p.TH * d.stride), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};

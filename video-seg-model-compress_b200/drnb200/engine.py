@@ -45,6 +45,11 @@ class ConvLayer:
         self.input_from = input_from    # index of the op whose output feeds this conv (None = previous)
         self.residual_from = residual_from
         self.out_f32 = False
+        self.keys = [key]               # state_dict conv keys this launch covers
+        self.x_cpitch = 0               # input lives in a wider NHWC tensor (channels per pixel), 0 = packed
+        self.res_cpitch = 0             # residual lives in a wider NHWC tensor
+        self.res_coffset = 0            # first residual channel inside that tensor
+        self.relu_n = 0                 # ReLU only on output channels < relu_n (0 = all, per self.relu)
         self.version = None
         self.row_ptr = self.kblk = self.w_packed = self.scale = self.shift = None
         self.n_live = 0
@@ -52,43 +57,85 @@ class ConvLayer:
         self.live_elems = 0             # surviving weight elements (Pruner.print_stats numerator)
         self.plans = {}
 
-    # ---- mask ingestion -----------------------------------------------------------------------
-    def weight_and_mask(self, mask_dict):
-        conv = self.conv
-        if hasattr(conv, "weight_orig") and hasattr(conv, "weight_mask"):   # torch.nn.utils.prune
-            return conv.weight_orig.detach(), conv.weight_mask.detach(), (
-                conv.weight_orig._version, conv.weight_mask._version)
-        w = conv.weight.detach()
-        if mask_dict is not None:
-            for k in (self.key + ".weight", "module." + self.key + ".weight"):
-                if k in mask_dict:
-                    m = mask_dict[k]
-                    return w, m, (w._version, id(m), m._version)
-        return w, None, (w._version,)
-
     def destroy_plans(self):
         lib = ffi.lib()
         for p in self.plans.values():
             lib.drnb200_conv_plan_destroy(p)
         self.plans = {}
 
-    def refresh(self, mask_dict, act_dtype, device):
-        """(re)build tile list, packed weights and BN affine if the parameters changed"""
-        w, m, ver = self.weight_and_mask(mask_dict)
-        bn = self.bn
-        ver = ver + (act_dtype, bn.weight._version, bn.bias._version, bn.running_mean._version,
-                     bn.running_var._version) if bn is not None else ver + (act_dtype,)
-        if ver == self.version:
-            return False
-        lib = ffi.lib()
-        self.destroy_plans()
-        O, I, kh, kw = w.shape
-        self.tile_o, self.tile_ci = _pick_tiles(I, O)
+    @staticmethod
+    def _conv_params(conv, key, mask_dict, device):
+        """(w32 [O,I,kh,kw], mask32 {0,1}, version) of one nn.Conv2d under the three mask sources"""
+        if hasattr(conv, "weight_orig") and hasattr(conv, "weight_mask"):   # torch.nn.utils.prune
+            w, m = conv.weight_orig.detach(), conv.weight_mask.detach()
+            ver = (w._version, m._version)
+        else:
+            w, m, ver = conv.weight.detach(), None, (conv.weight._version,)
+            if mask_dict is not None:
+                for k in (key + ".weight", "module." + key + ".weight"):
+                    if k in mask_dict:
+                        m = mask_dict[k]
+                        ver = (w._version, id(m), m._version)
+                        break
         w32 = w.to(device=device, dtype=torch.float32).contiguous()
         if m is None:
             mask32 = (w32 != 0).to(torch.float32)          # liveness from zeros (semantic_seg.py test path)
         else:
             mask32 = (m.to(device=device) != 0).to(torch.float32).contiguous()   # Hb masks may exceed 1
+        return w32, mask32, ver
+
+    @staticmethod
+    def _bn_affine(bn, channels, device):
+        """BatchNorm2d eval: y = (x-mean)/sqrt(var+eps)*gamma+beta (drn.py:7) as (scale, shift, version)"""
+        if bn is None:
+            return (torch.ones(channels, dtype=torch.float32, device=device),
+                    torch.zeros(channels, dtype=torch.float32, device=device), ())
+        inv = torch.rsqrt(bn.running_var.detach().to(device, torch.float32) + bn.eps)
+        scale = bn.weight.detach().to(device, torch.float32) * inv
+        shift = bn.bias.detach().to(device, torch.float32) - bn.running_mean.detach().to(device, torch.float32) * scale
+        ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version)
+        return scale.contiguous(), shift.contiguous(), ver
+
+    def version_key(self, mask_dict):
+        conv = self.conv
+        if hasattr(conv, "weight_orig") and hasattr(conv, "weight_mask"):
+            ver = (conv.weight_orig._version, conv.weight_mask._version)
+        else:
+            ver = (conv.weight._version,)
+            if mask_dict is not None:
+                for k in (self.key + ".weight", "module." + self.key + ".weight"):
+                    if k in mask_dict:
+                        ver = ver + (id(mask_dict[k]), mask_dict[k]._version)
+                        break
+        bn = self.bn
+        if bn is not None:
+            ver = ver + (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version)
+        return ver
+
+    def params(self, mask_dict, device):
+        """-> (w32, mask32, scale, shift) of this launch"""
+        w32, mask32, _ = self._conv_params(self.conv, self.key, mask_dict, device)
+        scale, shift, _ = self._bn_affine(self.bn, w32.shape[0], device)
+        return w32, mask32, scale, shift
+
+    @property
+    def out_channels(self):
+        return self.conv.out_channels
+
+    def dense_macs_per_pixel(self):
+        c = self.conv
+        return c.out_channels * c.in_channels * c.kernel_size[0] ** 2
+
+    def refresh(self, mask_dict, act_dtype, device):
+        """(re)build tile list, packed weights and BN affine if the parameters changed"""
+        ver = self.version_key(mask_dict) + (act_dtype, str(device))
+        if ver == self.version:
+            return False
+        lib = ffi.lib()
+        self.destroy_plans()
+        w32, mask32, self.scale, self.shift = self.params(mask_dict, device)
+        O, I, kh, kw = w32.shape
+        self.tile_o, self.tile_ci = _pick_tiles(I, O)
         n_ot, n_kb = O // self.tile_o, (I // self.tile_ci) * kh * kw
         self.row_ptr = torch.empty(n_ot + 1, dtype=torch.int32, device=device)
         self.kblk = torch.empty(max(1, n_ot * n_kb), dtype=torch.int32, device=device)
@@ -105,14 +152,6 @@ class ConvLayer:
                                            act_dtype, ffi.ptr(self.w_packed), st),
                   "pack_weights(%s)" % self.key)
         self.live_elems = int(torch.count_nonzero(w32 * mask32).item())
-        if bn is not None:      # BatchNorm2d eval: y = (x-mean)/sqrt(var+eps)*gamma+beta  (drn.py:7)
-            inv = torch.rsqrt(bn.running_var.detach().to(device, torch.float32) + bn.eps)
-            self.scale = (bn.weight.detach().to(device, torch.float32) * inv).contiguous()
-            self.shift = (bn.bias.detach().to(device, torch.float32)
-                          - bn.running_mean.detach().to(device, torch.float32) * self.scale).contiguous()
-        else:
-            self.scale = torch.ones(O, dtype=torch.float32, device=device)
-            self.shift = torch.zeros(O, dtype=torch.float32, device=device)
         self.version = ver
         return True
 
@@ -121,11 +160,12 @@ class ConvLayer:
         p = self.plans.get(k)
         if p is None:
             conv = self.conv
-            d = ffi.ConvDesc(N=N, H=H, W=W, Cin=conv.in_channels, Cout=conv.out_channels,
+            d = ffi.ConvDesc(N=N, H=H, W=W, Cin=conv.in_channels, Cout=self.out_channels,
                              ksize=conv.kernel_size[0], stride=conv.stride[0], dilation=conv.dilation[0],
                              relu=int(self.relu), has_residual=int(self.residual_from is not None),
                              act_dtype=act_dtype, out_f32=int(self.out_f32), tile_o=self.tile_o,
-                             tile_ci=self.tile_ci, impl=impl)
+                             tile_ci=self.tile_ci, impl=impl, x_cpitch=self.x_cpitch,
+                             res_cpitch=self.res_cpitch, res_coffset=self.res_coffset, relu_n=self.relu_n)
             h = C.c_void_p()
             ffi.check(ffi.lib().drnb200_conv_plan_create(
                 C.byref(h), C.byref(d), ffi.ptr(self.row_ptr), ffi.ptr(self.kblk), ffi.ptr(self.w_packed),
@@ -136,6 +176,62 @@ class ConvLayer:
     def out_hw(self, H, W):
         s = self.conv.stride[0]
         return (H - 1) // s + 1, (W - 1) // s + 1
+
+
+class FusedFirstConv(ConvLayer):
+    """conv1 (3x3, stride s) of a BasicBlock and the block's downsample (1x1, stride s; drn.py:181-186) as ONE
+    launch with output channels [conv1 | downsample]: the 1x1 projection reads exactly the centre tap of the
+    3x3 window (padding == dilation), so it is embedded as a 3x3 filter whose other eight taps are zero — dead
+    K-blocks that the tile list skips.  ReLU applies to the conv1 half only.  conv2 then takes its input from
+    channels [0, C) and its residual from channels [C, 2C) of the 2C-channel result."""
+
+    def __init__(self, key, block, input_from):
+        super().__init__(key + ".conv1", block.conv1, block.bn1, True, input_from=input_from)
+        self.ds_conv, self.ds_bn = block.downsample[0], block.downsample[1]
+        self.ds_key = key + ".downsample.0"
+        self.keys = [key + ".conv1", self.ds_key]
+        self.relu_n = block.conv1.out_channels
+
+    @staticmethod
+    def applicable(block):
+        ds = block.downsample
+        c1 = block.conv1
+        return (ds is not None and getattr(block, "residual", True) and c1.kernel_size == (3, 3)
+                and ds[0].kernel_size == (1, 1) and ds[0].stride == c1.stride
+                and ds[0].out_channels == c1.out_channels and ds[0].in_channels == c1.in_channels)
+
+    @property
+    def out_channels(self):
+        return 2 * self.conv.out_channels
+
+    def dense_macs_per_pixel(self):
+        c = self.conv
+        return c.out_channels * c.in_channels * 9 + c.out_channels * c.in_channels
+
+    def version_key(self, mask_dict):
+        ver = super().version_key(mask_dict)
+        ds, bn = self.ds_conv, self.ds_bn
+        if hasattr(ds, "weight_orig") and hasattr(ds, "weight_mask"):
+            ver = ver + (ds.weight_orig._version, ds.weight_mask._version)
+        else:
+            ver = ver + (ds.weight._version,)
+            if mask_dict is not None:
+                for k in (self.ds_key + ".weight", "module." + self.ds_key + ".weight"):
+                    if k in mask_dict:
+                        ver = ver + (id(mask_dict[k]), mask_dict[k]._version)
+                        break
+        return ver + (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version)
+
+    def params(self, mask_dict, device):
+        w1, m1, _ = self._conv_params(self.conv, self.key, mask_dict, device)
+        wd, md, _ = self._conv_params(self.ds_conv, self.ds_key, mask_dict, device)
+        s1, b1, _ = self._bn_affine(self.bn, w1.shape[0], device)
+        sd, bd, _ = self._bn_affine(self.ds_bn, wd.shape[0], device)
+        wd3, md3 = torch.zeros_like(w1), torch.zeros_like(m1)
+        wd3[:, :, 1, 1] = wd[:, :, 0, 0]
+        md3[:, :, 1, 1] = md[:, :, 0, 0]
+        return (torch.cat([w1, wd3]).contiguous(), torch.cat([m1, md3]).contiguous(),
+                torch.cat([s1, sd]).contiguous(), torch.cat([b1, bd]).contiguous())
 
 
 def _check_conv(conv, key):
@@ -169,8 +265,9 @@ class _Timed:
 class Engine:
     """builds and runs the launch list for one DRNSeg module"""
 
-    def __init__(self, seg_module, act_dtype="bf16", conv_impl=ffi.IMPL_AUTO):
+    def __init__(self, seg_module, act_dtype="bf16", conv_impl=ffi.IMPL_AUTO, fuse_downsample=True):
         self.m = seg_module
+        self.fuse_downsample = fuse_downsample    # [conv1 | 1x1 downsample] of a BasicBlock in one launch
         self.act_dtype = _DT[act_dtype] if isinstance(act_dtype, str) else int(act_dtype)
         self.conv_impl = conv_impl
         self.mask_dict = None
@@ -210,6 +307,15 @@ class Engine:
             if isinstance(mod, BasicBlock):
                 src = len(ops) - 1          # output index feeding this block (-1 = stem output)
                 _check_conv(mod.conv1, key + ".conv1"); _check_conv(mod.conv2, key + ".conv2")
+                if self.fuse_downsample and FusedFirstConv.applicable(mod):
+                    _check_conv(mod.downsample[0], key + ".downsample.0")
+                    planes = mod.conv1.out_channels
+                    ops.append(FusedFirstConv(key, mod, input_from=src))
+                    f = len(ops) - 1
+                    c2 = ConvLayer(key + ".conv2", mod.conv2, mod.bn2, True, residual_from=f, input_from=f)
+                    c2.x_cpitch, c2.res_cpitch, c2.res_coffset = 2 * planes, 2 * planes, planes
+                    ops.append(c2)
+                    return
                 ops.append(ConvLayer(key + ".conv1", mod.conv1, mod.bn1, True, input_from=src))
                 res = None
                 if getattr(mod, "residual", True):
@@ -345,8 +451,7 @@ class Engine:
             oh, ow = op.out_hw(ih, iw)
             shapes[i] = (oh, ow)
             px = N * oh * ow
-            c = op.conv
-            dense += px * c.out_channels * c.in_channels * c.kernel_size[0] ** 2
+            dense += px * op.dense_macs_per_pixel()
             live += px * op.live_elems
             tile += px * op.n_live * op.tile_o * op.tile_ci
         oh, ow = shapes[len(self.ops) - 1]
@@ -416,7 +521,7 @@ class Engine:
             oh, ow = op.out_hw(ih, iw)
             shapes[i] = (oh, ow)
             plan = op.plan(N, ih, iw, adt, self.conv_impl)
-            yo = take(N * oh * ow * op.conv.out_channels)
+            yo = take(N * oh * ow * op.out_channels)
             res = outs[op.residual_from] if op.residual_from is not None else None
             with timed(op.key):
                 ffi.check(lib.drnb200_conv_forward(plan, ffi.ptr(outs[src]), ffi.ptr(res), ffi.ptr(yo), st),
