@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRNB200_VERSION 101
+#define DRNB200_VERSION 102
 
 /* error codes */
 #define DRNB200_OK          0
@@ -139,6 +139,18 @@ int  drnb200_stem_plan_create(drnb200_stem_plan** out, const float* w_oihw, cons
                               void* stream);
 int  drnb200_stem_plan_forward(drnb200_stem_plan* plan, const float* x_nchw, void* y_nhwc, void* stream);
 void drnb200_stem_plan_destroy(drnb200_stem_plan* plan);
+/* Frame ingest fused into the stem: frames are uint8 HWC [N,H,W,3] as cv2 / PIL deliver them
+ * (seg_video_old.py:122-139); ToTensorVideoImage's `.float().div(255)` (data_transforms.py:256-281) and
+ * Normalize's `(x - mean) / std` (data_transforms.py:109-125, info.json) are applied through `lut`
+ * ([3][256] act_dtype values, DEVICE pointer, built by drnb200_ingest_lut and uploaded by the caller);
+ * tensor channel c reads byte c of the pixel (byte 2-c when bgr != 0).  Padding pixels are 0 after
+ * normalisation, exactly as Conv2d pads the normalised tensor.  Needs W % 16 == 0.  Output: same as
+ * drnb200_stem_plan_forward on the normalised float32 NCHW tensor rounded to act_dtype. */
+int  drnb200_stem_plan_forward_u8(drnb200_stem_plan* plan, const uint8_t* frames_nhwc, const uint16_t* lut,
+                                  int bgr, void* y_nhwc, void* stream);
+/* HOST function (no GPU): lut[c*256+b] = act_dtype(((float(b) / 255) - mean[c]) / std[c]), each step a
+ * correctly rounded fp32 operation like the reference's torch CPU transforms.  lut: host, 768 entries. */
+int  drnb200_ingest_lut(const float* mean, const float* std, int act_dtype, uint16_t* lut);
 int drnb200_stem_forward(const float* x_nchw, const float* w_oihw, const float* bn_scale,
                          const float* bn_shift, int N, int H, int W, int C0, int act_dtype,
                          void* y_nhwc, void* stream);
@@ -172,6 +184,14 @@ int drnb200_confusion(const uint8_t* pred, const void* label, int label_is_i64, 
                       int classes, int64_t* hist, void* stream);
 
 /* uint8 labels -> int64 (the dtype torch.max returns, semantic_seg.py:445) */
+/* Palette / overlay output: out[p] = palette[labels[p]] (`CITYSCAPE_PALETTE[pred]`,
+ * semantic_seg.py:52-72, :101-112; seg_video.py:168); labels >= n_colors take the last palette row.
+ * With frames != NULL (uint8 RGB, same pixels): out = rint(alpha*colour + (1-alpha)*frame) in separately
+ * rounded fp32 steps — the alpha=0.6 overlay seg_video.py:200-203 draws with matplotlib (matplotlib is not
+ * available here, so the blend rule is this library's definition, restated in oracle/frameio_oracle.py).
+ * labels [n_px] uint8, palette [n_colors][3] uint8 (device), out [n_px][3] uint8; n_px % 4 == 0. */
+int drnb200_colorize(const uint8_t* labels, int64_t n_px, const uint8_t* palette, int n_colors,
+                     const uint8_t* frames_or_null, float alpha, uint8_t* out_rgb, void* stream);
 int drnb200_labels_to_i64(const uint8_t* labels, int64_t n, int64_t* out, void* stream);
 
 #ifdef __cplusplus

@@ -443,3 +443,90 @@ def test_full_size_properties():
     agree = (c[0] == a[0]).float().mean().item()
     print("tcgen05 vs direct label agreement at 1024x2048: %.6f" % agree)
     assert agree >= 0.9995
+
+
+# ------------------------------------------------------------------ rows either side of the path
+def _u8_frames(n, h, w, seed, smooth=False):
+    rng = np.random.RandomState(seed)
+    if smooth:
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = (np.sin(yy / 9.0)[..., None] * 60 + np.cos(xx / 13.0)[..., None] * 60 + 128
+                + rng.randn(1, 1, 3) * 20)
+        f = np.clip(base[None] + rng.randn(n, h, w, 3) * 3, 0, 255)
+        return f.astype(np.uint8)
+    return rng.randint(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("act", ["fp16", "bf16"])
+@pytest.mark.parametrize("hw", [(64, 128), (136, 48), (72, 208)])
+def test_uint8_ingest_is_bit_identical_to_normalised_float_frames(act, hw):
+    """frame ingest fused into the stem: predict(uint8 HWC) == predict(ToTensor+Normalize of the same frames)
+    bit for bit (labels AND logits), because the table holds exactly the act_dtype rounding of the fp32 transform"""
+    from oracle import frameio_oracle
+    fx = np.load(golden("frameio.npz"))
+    mean, std = fx["mean"], fx["std"]
+    model, sd, _ = _gate_case("drn_d_22", 64, 128, 1, True, act, seed=21)
+    frames = _u8_frames(2, hw[0], hw[1], seed=hw[0], smooth=(hw[1] == 48))
+    x = frameio_oracle.ingest(frames, mean, std)                       # the reference's transform (CPU)
+    model.set_ingest(mean, std)
+    fd = torch.from_numpy(frames).to(dev())
+    with torch.no_grad():
+        lab_u8 = model.predict(fd)
+        lab_f32 = model.predict(x.to(dev()))
+        lp_u8, seg_u8 = model(fd)
+        lp_f32, seg_f32 = model(x.to(dev()))
+    assert torch.equal(lab_u8, lab_f32) and torch.equal(seg_u8, seg_f32) and torch.equal(lp_u8, lp_f32)
+    # BGR frames (cv2 order) with bgr=True give the same result as the RGB frames
+    model.set_ingest(mean, std, bgr=True)
+    lab_bgr = model.predict(torch.from_numpy(np.ascontiguousarray(frames[..., ::-1])).to(dev()))
+    assert torch.equal(lab_bgr, lab_u8)
+    # and the whole thing still tracks the oracle on the normalised frames
+    ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
+    assert rel_err(seg_u8.cpu(), ref_seg) <= (LOGIT_RTOL if act == "fp16" else 2 * LOGIT_RTOL)
+
+
+def test_uint8_ingest_validation():
+    model, sd, _ = _gate_case("drn_d_22", 64, 128, 1, False, "fp16", seed=22)
+    frames = torch.zeros(1, 64, 128, 3, dtype=torch.uint8, device=dev())
+    with pytest.raises(ffi.Drnb200Error):
+        model.predict(frames)                                           # set_ingest() not called
+    model.set_ingest((0.3, 0.3, 0.3), (0.2, 0.2, 0.2))
+    assert model.predict(frames).shape == (1, 64, 128)
+    with pytest.raises(ffi.Drnb200Error):
+        model.predict(torch.zeros(1, 64, 72, 3, dtype=torch.uint8, device=dev()))    # W % 16 != 0
+    with pytest.raises(ffi.Drnb200Error):
+        model.predict(torch.zeros(1, 3, 64, 128, dtype=torch.uint8, device=dev()))   # not HWC
+
+
+def test_colorize_and_overlay_bit_exact():
+    from oracle import frameio_oracle
+    fx = np.load(golden("frameio.npz"))
+    pred = fx["pred"].astype(np.uint8)
+    got = drnb200.colorize(torch.from_numpy(pred).to(dev()))
+    assert np.array_equal(got.cpu().numpy(), fx["color"])               # the real reference's CITYSCAPE_PALETTE[pred]
+    rng = np.random.RandomState(3)
+    lab = rng.randint(0, 19, size=(3, 40, 52)).astype(np.uint8)
+    lab[0, 0, :7] = [255, 19, 20, 0, 18, 200, 7]                        # ignore / out-of-palette labels -> last row
+    frames = rng.randint(0, 256, size=(3, 40, 52, 3), dtype=np.uint8)
+    ld, fd = torch.from_numpy(lab).to(dev()), torch.from_numpy(frames).to(dev())
+    assert np.array_equal(drnb200.colorize(ld).cpu().numpy(), frameio_oracle.colorize(lab))
+    for alpha in (0.6, 0.0, 1.0, 0.37):
+        assert np.array_equal(drnb200.overlay(ld, fd, alpha).cpu().numpy(),
+                              frameio_oracle.overlay(lab, frames, alpha)), alpha
+    pal = rng.randint(0, 256, size=(7, 3), dtype=np.uint8)
+    assert np.array_equal(drnb200.colorize(ld, pal).cpu().numpy(), frameio_oracle.colorize(lab, pal))
+    assert drnb200.colorize(torch.zeros(0, 4, dtype=torch.uint8, device=dev())).shape == (0, 4, 3)
+
+
+def test_full_size_uint8_ingest():
+    """1024x2048: the fused uint8 ingest equals the float path fed with the reference's transform of the same frames"""
+    from oracle import frameio_oracle
+    fx = np.load(golden("frameio.npz"))
+    model, sd, _ = _gate_case("drn_d_22", 64, 128, 1, True, "fp16", seed=23)
+    frames = _u8_frames(1, 1024, 2048, seed=5, smooth=True)
+    model.set_ingest(fx["mean"], fx["std"])
+    a = model.predict(torch.from_numpy(frames).to(dev()))
+    b = model.predict(frameio_oracle.ingest(frames, fx["mean"], fx["std"]).to(dev()))
+    assert torch.equal(a, b)
+    col = drnb200.overlay(a, torch.from_numpy(frames).to(dev()))
+    assert np.array_equal(col.cpu().numpy(), frameio_oracle.overlay(a.cpu().numpy(), frames))

@@ -229,7 +229,26 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), name
     lib = ffi.lib()
-    assert lib.drnb200_version() == 101
+    assert lib.drnb200_version() == 102
     # argument validation happens before any CUDA call, so it is testable here
     assert lib.drnb200_compact_mask(None, 8, 8, 3, 3, 8, 8, None, None, None, None) == -1
     assert b"null pointer" in lib.drnb200_last_error()
+
+
+@pytest.mark.parametrize("act", ["fp16", "bf16"])
+def test_ingest_table_host_function_is_bit_exact(act):
+    """drnb200_ingest_lut is a HOST function of the C ABI (no GPU): it must equal the reference's transform of every
+    byte value (fixture from the real data_transforms.py) rounded once to the activation dtype"""
+    fx = np.load(golden("frameio.npz"))
+    lut = drnb200.ingest_lut(fx["mean"], fx["std"], {"bf16": 0, "fp16": 1}[act])
+    ref = torch.from_numpy(fx["lut"]).to(torch.float16 if act == "fp16" else torch.bfloat16).view(torch.int16)
+    assert lut.shape == (3, 256) and torch.equal(lut, ref)
+    assert drnb200.CITYSCAPE_PALETTE.shape == (20, 3) and np.array_equal(drnb200.CITYSCAPE_PALETTE, fx["palette"])
+
+
+def test_frameio_fails_loudly_on_cpu_tensors():
+    with pytest.raises(ffi.Drnb200Error):
+        drnb200.colorize(torch.zeros(4, 4, dtype=torch.uint8))
+    model = drnb200.DRNSeg("drn_d_22", 19, pretrained_model=None, pretrained=False).eval()
+    with pytest.raises(ffi.Drnb200Error):
+        model.predict(torch.zeros(1, 16, 16, 3, dtype=torch.uint8))

@@ -105,3 +105,22 @@ def test_swizzle_is_a_permutation():
     for pitch in (32, 64, 128):
         offs = {compact_oracle.swizzle_offset(r, c, pitch) for r in range(64) for c in range(pitch // 16)}
         assert offs == set(range(0, 64 * pitch, 16))
+
+
+# ------------------------------------------------------------------ rows either side of the path
+def test_frame_ingest_matches_reference_transforms():
+    """oracle ingest == ToTensorVideoImage + Normalize of the reference (data_transforms.py), bit for bit"""
+    from oracle import frameio_oracle
+    fx = np.load(golden("frameio.npz"))
+    x = frameio_oracle.ingest(fx["frame"][None], fx["mean"], fx["std"])[0].numpy()
+    assert x.dtype == np.float32 and np.array_equal(x, fx["x"])
+    assert np.array_equal(frameio_oracle.ingest_table(fx["mean"], fx["std"]).numpy(), fx["lut"])
+
+
+def test_palette_matches_reference():
+    from oracle import frameio_oracle
+    fx = np.load(golden("frameio.npz"))
+    assert np.array_equal(frameio_oracle.CITYSCAPE_PALETTE, fx["palette"])
+    assert np.array_equal(frameio_oracle.colorize(fx["pred"]), fx["color"])
+    # out-of-palette labels (ignore = 255) take the last row, the rule seg_video.py spells out in a comment
+    assert np.array_equal(frameio_oracle.colorize(np.array([255, 19, 18])), fx["palette"][[19, 19, 18]])

@@ -232,6 +232,19 @@ static int run_stem(int dt, int use_plan = 0, int N = 2, int H = 20, int W = 72)
   const int C0 = 16;
   std::vector<float> x((size_t)N * 3 * H * W), w(C0 * 147), sc(C0), sh(C0);
   for (auto& v : x) v = frand();
+  // use_plan == 2: uint8 HWC frames through the ingest table; x becomes the normalised frame the table defines
+  std::vector<uint8_t> xu8;
+  std::vector<uint16_t> lut(768);
+  const int bgr = (H & 1);
+  if (use_plan == 2) {
+    const float mean[3] = {0.29010095f, 0.32808145f, 0.28696394f}, sd[3] = {0.18295405f, 0.18656561f, 0.18447509f};
+    API(drnb200_ingest_lut(mean, sd, dt, lut.data()));
+    xu8.resize((size_t)N * H * W * 3);
+    for (auto& b : xu8) b = (uint8_t)(int)((frand() * 0.5f + 0.5f) * 255.99f);
+    for (int n = 0; n < N; ++n) for (int ci = 0; ci < 3; ++ci) for (int yy = 0; yy < H; ++yy) for (int xx = 0; xx < W; ++xx)
+      x[(((size_t)n * 3 + ci) * H + yy) * W + xx] =
+          from16(lut[ci * 256 + xu8[(((size_t)n * H + yy) * W + xx) * 3 + (bgr ? 2 - ci : ci)]], dt);
+  }
   for (auto& v : w) v = use_plan ? round16(frand() * 0.1f, DRNB200_BF16) : frand() * 0.1f;
   if (use_plan) for (auto& v : x) v = round16(v, dt);   // the tensor-core stem rounds the frame to act_dtype
   for (int c = 0; c < C0; ++c) { sc[c] = 1.0f + 0.3f * frand(); sh[c] = 0.2f * frand(); }
@@ -241,12 +254,16 @@ static int run_stem(int dt, int use_plan = 0, int N = 2, int H = 20, int W = 72)
   if (use_plan) {
     drnb200_stem_plan* sp = nullptr;
     API(drnb200_stem_plan_create(&sp, dw, dsc, dsh, N, H, W, C0, dt, 0));
-    API(drnb200_stem_plan_forward(sp, dx, dy, 0));
+    uint8_t* du8 = nullptr; uint16_t* dlut = nullptr;
+    if (use_plan == 2) { du8 = dev_upload(xu8); dlut = dev_upload(lut); }
+    auto fwd = [&]() { return use_plan == 2 ? drnb200_stem_plan_forward_u8(sp, du8, dlut, bgr, dy, 0)
+                                            : drnb200_stem_plan_forward(sp, dx, dy, 0); };
+    API(fwd());
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("  stem kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < 5; ++i) API(drnb200_stem_plan_forward(sp, dx, dy, 0));
+    for (int i = 0; i < 5; ++i) API(fwd());
     CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
     float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("  stem (tcgen05) time %.3f ms\n", ms / 5);
@@ -410,7 +427,7 @@ int main(int argc, char** argv) {
   const std::string name = argv[1];
   if (name == "list") {
     for (const auto& c : kCases) printf("%s\n", c.name);
-    printf("stem_bf16\nstem_f16\nstem_tc_bf16\nstem_tc_f16\nhead_bf16\nhead_f16\nhist\n");
+    printf("stem_bf16\nstem_f16\nstem_tc_bf16\nstem_tc_f16\nstem_tc_tall\nstem_u8_f16\nstem_u8_bf16\nhead_bf16\nhead_f16\nhist\n");
     return 0;
   }
   int dev_count = 0;
@@ -422,6 +439,10 @@ int main(int argc, char** argv) {
   if (name == "stem_tc_bf16") return run_stem(DRNB200_BF16, 1);
   if (name == "stem_tc_f16") return run_stem(DRNB200_F16, 1, 1, 37, 100);
   if (name == "stem_tc_big") return run_stem(DRNB200_F16, 1, 8, 1024, 2048);
+  if (name == "stem_tc_tall") return run_stem(DRNB200_BF16, 1, 2, 264, 40);
+  if (name == "stem_u8_f16") return run_stem(DRNB200_F16, 2, 2, 40, 64);
+  if (name == "stem_u8_bf16") return run_stem(DRNB200_BF16, 2, 1, 133, 48);
+  if (name == "stem_u8_big") return run_stem(DRNB200_F16, 2, 8, 1024, 2048);
   if (name == "head_bf16") return run_head(DRNB200_BF16, 2, 5, 9);
   if (name == "head_f16") return run_head(DRNB200_F16, 1, 16, 8);
   if (name == "hist") return run_hist();

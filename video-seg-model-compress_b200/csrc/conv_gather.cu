@@ -499,12 +499,20 @@ extern "C" int drnb200_stem_plan_forward(drnb200_stem_plan* plan, const float* x
                                          void* stream) {
   DRN_REQUIRE(plan && x_nchw && y_nhwc, "stem_plan_forward: null pointer");
   if (plan->tx)
-    return stem_tx_forward(plan->tx, x_nchw, y_nhwc, plan->d_scale, plan->d_shift, plan->N, plan->H, plan->W,
-                           plan->act_dtype, (cudaStream_t)stream);
+    return stem_tx_forward(plan->tx, x_nchw, 0, nullptr, 0, y_nhwc, plan->d_scale, plan->d_shift, plan->N, plan->H,
+                           plan->W, plan->act_dtype, (cudaStream_t)stream);
   GatherParams p{};
   p.x = x_nchw; p.y = y_nhwc; p.w_packed = reinterpret_cast<const uint8_t*>(plan->d_wpacked);
   p.kblk = plan->d_kblk; p.scale = plan->d_scale; p.shift = plan->d_shift; p.n_kb = G_MAX_KB;
   p.N = plan->N; p.H = plan->H; p.W = plan->W; p.OH = plan->H; p.OW = plan->W; p.Cout = 16;
   p.stride = 1; p.relu = 1; p.stem = 1;
   return gather_launch(p, plan->act_dtype, plan->cache, (cudaStream_t)stream);
+}
+
+extern "C" int drnb200_stem_plan_forward_u8(drnb200_stem_plan* plan, const uint8_t* frames_nhwc,
+                                            const uint16_t* lut, int bgr, void* y_nhwc, void* stream) {
+  DRN_REQUIRE(plan && frames_nhwc && lut && y_nhwc, "stem_plan_forward_u8: null pointer");
+  DRN_REQUIRE(plan->tx, "stem_plan_forward_u8: needs the Toeplitz stem (unset DRNB200_STEM=gather)");
+  return stem_tx_forward(plan->tx, frames_nhwc, 1, lut, bgr ? 1 : 0, y_nhwc, plan->d_scale, plan->d_shift, plan->N,
+                         plan->H, plan->W, plan->act_dtype, (cudaStream_t)stream);
 }

@@ -69,6 +69,6 @@ constexpr int TC_MODE_HALO = 4;
 struct StemTxState;
 int stem_tx_create(StemTxState** out, const float* w_oihw, int act_dtype, cudaStream_t st);
 void stem_tx_destroy(StemTxState* s);
-int stem_tx_forward(StemTxState* s, const float* x, void* y, const float* scale, const float* shift, int N,
-                    int H, int W, int act_dtype, cudaStream_t st);
+int stem_tx_forward(StemTxState* s, const void* x, int src_kind, const uint16_t* lut, int bgr, void* y,
+                    const float* scale, const float* shift, int N, int H, int W, int act_dtype, cudaStream_t st);
 }  // namespace drnb200

@@ -11,9 +11,17 @@
 // the halo [3][134 rows][16 x 16-bit], SWIZZLE_32B.  (Measured on B200: the UMMA swizzle XOR uses absolute
 // shared-memory address bits, so such shifted windows need no base offset; see conv_halo.cu.)
 // Per tile: one TMA box {16, 134, 3} of fp32 input -> 8 warps convert it to the 16-bit SWIZZLE_32B halo ->
-// 21 tcgen05.mma (M=128 rows, N=128 = 8 pixels x 16 couts, K=16) -> 4+4 epilogue warps (thread = image row:
-// 8 pixels x 16 channels = 256 contiguous bytes).  The im2col-gather stem this replaces moved 147 elements
-// per output pixel through shared memory (0.87 ms per 8-frame batch); this one moves ~6.
+// 21 tcgen05.mma (M=128 rows, N=128 = 8 pixels x 16 couts, K=16) -> 4+4 epilogue warps (thread = image row)
+// that stage 4-pixel half tiles ([128 rows][128 B], SWIZZLE_128B) in shared memory for one TMA store each:
+// a thread owns a whole image row of the tile, so direct global stores would touch 32 cache lines per warp
+// instruction (measured: 0.26 ms per 8-frame batch with them, 0.12 ms with the stores removed).
+// The im2col-gather stem this replaces moved 147 elements per output pixel through shared memory (0.87 ms).
+//
+// SRC_U8 variant (frame ingest): the input is the uint8 HWC frame as cv2/PIL deliver it
+// (seg_video_old.py:122-139); ToTensorVideoImage's /255 and Normalize's (x-mean)/std
+// (data_transforms.py:109-125, :256-281) are a 3x256-entry table of act_dtype values built on the host with
+// the same fp32 operations (drnb200_ingest_lut), looked up by the convert warps; pixels outside the frame
+// become 0 (the conv pads AFTER normalisation).
 #include "conv_internal.cuh"
 #include <algorithm>
 #include <cudaTypedefs.h>
@@ -24,45 +32,67 @@ namespace drnb200 {
 constexpr int TX_ROWS = 128;                 // tile height (UMMA M)
 constexpr int TX_COLS = 8;                   // tile width in pixels
 constexpr int TX_HROWS = TX_ROWS + 6;        // halo rows
-constexpr int TX_HW = 16;                    // halo columns: x0-4 .. x0+11
+constexpr int TX_PW = 24;                    // halo columns of a PAIR of x-adjacent tiles: x0-4 .. x0+19
 constexpr int TX_SEG = 21;                   // (ci, ky) segments = K-steps of 16
 constexpr int TX_PLANE = 17 * 256;           // 134 rows x 32 B, rounded up to the 256-byte swizzle period
-constexpr int TX_A_BYTES = 3 * TX_PLANE;     // 16-bit halo (UMMA A operand)
-constexpr int TX_F_BYTES = 3 * TX_HROWS * TX_HW * 4;   // fp32 halo as TMA delivers it
+constexpr int TX_A_BYTES = 3 * TX_PLANE;     // 16-bit halo of ONE tile (UMMA A operand)
+constexpr int TX_A_STRIDE = (TX_A_BYTES + 1023) & ~1023;
+constexpr int TX_F_BYTES = 3 * TX_HROWS * TX_PW * 4;   // fp32 halo of a tile pair as TMA delivers it
+constexpr int TX_U8_ROW = 112;               // uint8 halo row of a pair: 4 B slack + 24 px x 3 B = 76 B, padded so
+                                             // that the row pitch (28 words) spreads rows over the banks
+constexpr int TX_U8_BYTES = TX_U8_ROW * TX_HROWS;
 constexpr int TX_B_BYTES = TX_SEG * 128 * 32;          // resident Toeplitz weights
-constexpr int TX_RING = 3;                   // fp32 halo ring
-constexpr int TX_ABUF = 2;                   // 16-bit halo buffers
-constexpr int TX_ACC = 2;                    // TMEM accumulators (128 columns each)
+constexpr int TX_MAX_RING = 4, TX_MAX_ABUF = 4;
+constexpr int TX_ACC = 4;                    // TMEM accumulators (128 columns each): two per epilogue group
 constexpr int TX_CVT_WARPS = 8;
 constexpr int TX_W_MMA = TX_CVT_WARPS, TX_W_TMA = TX_CVT_WARPS + 1, TX_W_EPI = TX_CVT_WARPS + 2;
 constexpr int TX_THREADS = (TX_W_EPI + 8) * 32;
+constexpr int TX_STAGE = 128 * 128;          // epilogue staging buffer: 128 rows x 4 pixels x 16 ch x 2 B
+constexpr int SRC_F32 = 0, SRC_U8 = 1;
+__host__ __device__ constexpr int tx_f_stride(int src) {
+  return src == SRC_U8 ? ((TX_U8_BYTES + 127) & ~127) : ((TX_F_BYTES + 127) & ~127);
+}
+// staging buffers per epilogue group (one: the TMEM loads and BN math of the next half tile overlap the store's read)
+__host__ __device__ constexpr int tx_stg_bufs(int) { return 1; }
+// pipeline depths: input halo ring (pairs) and 16-bit halo buffers (tiles); the uint8 halo is 2.6x smaller.
+// Measured floors per 8 x 1024 x 2048 frames: TMEM read-out 0.06 ms (64 B/clk/SM), MMA operand reads from shared
+// memory ~0.08 ms, both variants end at 0.18-0.22 ms because the stages share the shared-memory bandwidth.
+__host__ __device__ constexpr int tx_ring(int src) { return src == SRC_U8 ? 3 : 2; }
+__host__ __device__ constexpr int tx_abufs(int src) { return src == SRC_U8 ? 4 : 2; }
+__host__ __device__ constexpr size_t tx_smem_bytes(int src) {
+  return 1024 + (size_t)tx_abufs(src) * TX_A_STRIDE + 2 * tx_stg_bufs(src) * TX_STAGE + TX_B_BYTES +
+         (size_t)tx_ring(src) * tx_f_stride(src);
+}
 
 struct StemTxParams {
-  const float* x;
-  uint16_t* y;
+  const uint16_t* lut;          // SRC_U8: [3][256] act_dtype values of ((b/255) - mean[c]) / std[c]
+  int bgr;                      // SRC_U8: tensor channel c reads byte 2-c of the pixel
   const uint8_t* w_packed;      // 21 tiles of 128 x 16 (32-byte rows, SWIZZLE_32B)
   const float* scale;
   const float* shift;
-  int N, H, W, tiles_x, tiles_y, total_tiles;
+  int N, H, W, pairs_x, tiles_y, total_pairs;
   uint32_t magic_x, magic_y, idesc;
+  int dbg;                      // timing diagnostics (DRNB200_DBG bits, results become invalid): 1 skip global stores,
+                                // 2 skip convert, 4 one MMA per tile, 8 skip proxy fence, 16 skip BN math, 32 skip staging
 };
 
 struct __align__(16) TxSync {
   alignas(16) float scale[16];
   alignas(16) float shift[16];
-  uint64_t f_full[TX_RING], f_empty[TX_RING], a_full[TX_ABUF], a_empty[TX_ABUF], t_full[TX_ACC],
+  alignas(16) uint16_t lut[768];
+  uint64_t f_full[TX_MAX_RING], f_empty[TX_MAX_RING], a_full[TX_MAX_ABUF], a_empty[TX_MAX_ABUF], t_full[TX_ACC],
       t_empty[TX_ACC], w_full;
   uint32_t tmem_base, pad;
 };
 
-struct TxTile { int n, x0, y0; };
+struct TxTile { int n, x0, y0; };          // x0 = left column of the PAIR (multiple of 16)
 __device__ __forceinline__ TxTile tx_decode(const StemTxParams& p, int t) {
   TxTile c;
-  const int q1 = p.tiles_x == 1 ? t : (int)__umulhi((uint32_t)t, p.magic_x);
-  const int txi = t - q1 * p.tiles_x;
+  const int q1 = p.pairs_x == 1 ? t : (int)__umulhi((uint32_t)t, p.magic_x);
+  const int txi = t - q1 * p.pairs_x;
   c.n = p.tiles_y == 1 ? q1 : (int)__umulhi((uint32_t)q1, p.magic_y);
   const int tyi = q1 - c.n * p.tiles_y;
-  c.x0 = txi * TX_COLS; c.y0 = tyi * TX_ROWS;
+  c.x0 = txi * 2 * TX_COLS; c.y0 = tyi * TX_ROWS;
   return c;
 }
 
@@ -78,21 +108,62 @@ template <> __device__ __forceinline__ uint32_t pack2<DRNB200_BF16>(float lo, fl
   return r;
 }
 
+// 8 pixels of tensor channel CH out of 24 interleaved bytes (6 words), through the normalisation table
+template <int CH>
+__device__ __forceinline__ uint4 tx_u8_lookup(const uint32_t (&wd)[6], const uint16_t* lut, int xb, int W,
+                                              bool rowok) {
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    const int i0 = 3 * j + CH, i1 = 3 * (j + 1) + CH;
+    const uint32_t b0 = (wd[i0 >> 2] >> ((i0 & 3) * 8)) & 0xFFu, b1 = (wd[i1 >> 2] >> ((i1 & 3) * 8)) & 0xFFu;
+    const uint32_t v0 = (rowok && (unsigned)(xb + j) < (unsigned)W) ? lut[b0] : 0u;
+    const uint32_t v1 = (rowok && (unsigned)(xb + j + 1) < (unsigned)W) ? lut[b1] : 0u;
+    o[j >> 1] = v0 | (v1 << 16);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// BN + ReLU + pack of one pixel's 16 channels (accumulator columns) -> two 16-byte chunks
 template <int DT>
+__device__ __forceinline__ void tx_bn_pack(const uint32_t* v, const TxSync* sync, uint4& lo, uint4& hi) {
+  uint32_t w[8];
+#pragma unroll
+  for (int e4 = 0; e4 < 4; ++e4) {
+    const float4 sc = *reinterpret_cast<const float4*>(&sync->scale[4 * e4]);
+    const float4 sh = *reinterpret_cast<const float4*>(&sync->shift[4 * e4]);
+    const float a0 = fmaxf(fmaf(__uint_as_float(v[4 * e4]), sc.x, sh.x), 0.f);
+    const float a1 = fmaxf(fmaf(__uint_as_float(v[4 * e4 + 1]), sc.y, sh.y), 0.f);
+    const float a2 = fmaxf(fmaf(__uint_as_float(v[4 * e4 + 2]), sc.z, sh.z), 0.f);
+    const float a3 = fmaxf(fmaf(__uint_as_float(v[4 * e4 + 3]), sc.w, sh.w), 0.f);
+    w[2 * e4] = pack2<DT>(a0, a1);
+    w[2 * e4 + 1] = pack2<DT>(a2, a3);
+  }
+  lo = make_uint4(w[0], w[1], w[2], w[3]);
+  hi = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+template <int DT, int SRC>
 __global__ void __launch_bounds__(TX_THREADS, 1)
-stem_tx_kernel(const __grid_constant__ CUtensorMap tmap_x, const StemTxParams p) {
+stem_tx_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
+               const StemTxParams p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int F_STRIDE = tx_f_stride(SRC);
+  constexpr int STG = tx_stg_bufs(SRC);
+  constexpr int TX_RING = tx_ring(SRC), TX_ABUF = tx_abufs(SRC);
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* abuf = smem;                                          // TX_ABUF x TX_A_BYTES (1024-aligned)
-  uint8_t* wsm = abuf + TX_ABUF * ((TX_A_BYTES + 1023) & ~1023); // TX_B_BYTES
-  uint8_t* fbuf = wsm + TX_B_BYTES;                              // TX_RING x fp32 halo
-  constexpr int F_STRIDE = (TX_F_BYTES + 127) & ~127;
-  TxSync* sync = reinterpret_cast<TxSync*>(fbuf + TX_RING * F_STRIDE);
+  uint8_t* abuf = smem;                                          // TX_ABUF x TX_A_STRIDE (1024-aligned)
+  uint8_t* stage = abuf + TX_ABUF * TX_A_STRIDE;                 // 2 groups x STG x TX_STAGE (1024-aligned)
+  uint8_t* wsm = stage + 2 * STG * TX_STAGE;                     // TX_B_BYTES
+  uint8_t* fbuf = wsm + TX_B_BYTES;                              // TX_RING x input halo of a tile pair
+  __shared__ TxSync sync_s;
+  TxSync* sync = &sync_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_y);
     for (int b = 0; b < TX_RING; ++b) { mbar_init(&sync->f_full[b], 1); mbar_init(&sync->f_empty[b], TX_CVT_WARPS); }
     for (int b = 0; b < TX_ABUF; ++b) { mbar_init(&sync->a_full[b], TX_CVT_WARPS); mbar_init(&sync->a_empty[b], 1); }
     for (int b = 0; b < TX_ACC; ++b) { mbar_init(&sync->t_full[b], 1); mbar_init(&sync->t_empty[b], 4); }
@@ -100,12 +171,14 @@ stem_tx_kernel(const __grid_constant__ CUtensorMap tmap_x, const StemTxParams p)
     mbar_fence_init();
   }
   if (tid < 16) { sync->scale[tid] = __ldg(p.scale + tid); sync->shift[tid] = __ldg(p.shift + tid); }
+  if (SRC == SRC_U8)
+    for (int i = tid; i < 768; i += TX_THREADS) sync->lut[i] = __ldg(p.lut + i);
   if (warp == TX_W_MMA) {
     tmem_alloc(&sync->tmem_base, TX_ACC * 128);
     tmem_relinquish();
   }
   // the pad rows/bytes of the 16-bit halo planes are never written by the converters: clear them once
-  for (int i = tid; i < TX_ABUF * ((TX_A_BYTES + 1023) & ~1023) / 16; i += TX_THREADS)
+  for (int i = tid; i < TX_ABUF * TX_A_STRIDE / 16; i += TX_THREADS)
     reinterpret_cast<uint4*>(abuf)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -113,6 +186,7 @@ stem_tx_kernel(const __grid_constant__ CUtensorMap tmap_x, const StemTxParams p)
   tc_fence_after();
   const uint32_t tmem_base = sync->tmem_base;
 
+  // Every role walks the same sequence: pairs pr = blockIdx.x, +gridDim.x, ...; each pair = two tiles (sub 0, 1).
   if (warp == TX_W_TMA) {
     // ================================================================= TMA producer (warp-uniform loop)
     if (elect_one()) {
@@ -121,14 +195,21 @@ stem_tx_kernel(const __grid_constant__ CUtensorMap tmap_x, const StemTxParams p)
     }
     int b = 0;
     uint32_t ph = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TxTile c = tx_decode(p, t);
+    for (int pr = blockIdx.x; pr < p.total_pairs; pr += gridDim.x) {
+      const TxTile c = tx_decode(p, pr);
       mbar_wait(&sync->f_empty[b], ph ^ 1u);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&sync->f_full[b], TX_F_BYTES);
-        // tensor {W, H, 3, N} fp32; box {16, 134, 3, 1}; x origin x0-4 keeps the box 16-byte aligned;
-        // elements outside the image are zero-filled = the conv padding
-        tma_load_4d(&tmap_x, &sync->f_full[b], fbuf + b * F_STRIDE, c.x0 - 4, c.y0 - 3, 0, c.n);
+        if (SRC == SRC_F32) {
+          mbar_arrive_expect_tx(&sync->f_full[b], TX_F_BYTES);
+          // tensor {W, H, 3, N} fp32; box {24, 134, 3, 1}; x origin x0-4 keeps the box 16-byte aligned;
+          // elements outside the image are zero-filled = the conv padding
+          tma_load_4d(&tmap_x, &sync->f_full[b], fbuf + b * F_STRIDE, c.x0 - 4, c.y0 - 3, 0, c.n);
+        } else {
+          mbar_arrive_expect_tx(&sync->f_full[b], TX_U8_BYTES);
+          // tensor {3W bytes, H, N, 1} uint8; box {112, 134, 1, 1} from byte 3*(x0-4) - 4 of the row (16-byte
+          // aligned because x0 % 16 == 0; the converters skip the 4 slack bytes)
+          tma_load_4d(&tmap_x, &sync->f_full[b], fbuf + b * F_STRIDE, (c.x0 - 4) * 3 - 4, c.y0 - 3, c.n, 0);
+        }
       }
       __syncwarp();
       if (++b == TX_RING) { b = 0; ph ^= 1u; }
@@ -138,92 +219,136 @@ stem_tx_kernel(const __grid_constant__ CUtensorMap tmap_x, const StemTxParams p)
     mbar_wait(&sync->w_full, 0);
     const uint64_t d_hi = umma_smem_desc(0u, 32);           // K-major, 32-byte rows, SBO = 256
     const uint32_t w16 = smem_u32(wsm) >> 4;
-    int i = 0, b = 0;
-    uint32_t ph = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-      const int acc = i % TX_ACC;
-      mbar_wait(&sync->a_full[b], ph);
-      mbar_wait(&sync->t_empty[acc], ((uint32_t)(i / TX_ACC) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t a16 = smem_u32(abuf + b * ((TX_A_BYTES + 1023) & ~1023)) >> 4;
-      if (elect_one()) {
+    int b = 0, acc = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int pr = blockIdx.x; pr < p.total_pairs; pr += gridDim.x) {
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        mbar_wait(&sync->a_full[b], ph);
+        mbar_wait(&sync->t_empty[acc], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t a16 = smem_u32(abuf + b * TX_A_STRIDE) >> 4;
+        if (elect_one()) {
 #pragma unroll
-        for (int s = 0; s < TX_SEG; ++s) {
-          const int ci = s / 7, ky = s % 7;                 // A window: plane ci, shifted down by ky rows
-          umma_f16(tmem_base + (uint32_t)acc * 128u,
-                   d_hi | (uint64_t)(a16 + (uint32_t)(ci * TX_PLANE + ky * 32) / 16u),
-                   d_hi | (uint64_t)(w16 + (uint32_t)s * (128u * 32u / 16u)), p.idesc, s > 0 ? 1u : 0u);
+          for (int s = 0; s < TX_SEG; ++s) {
+            if ((p.dbg & 4) && s > 0) break;
+            const int ci = s / 7, ky = s % 7;               // A window: plane ci, shifted down by ky rows
+            umma_f16(tmem_base + (uint32_t)acc * 128u,
+                     d_hi | (uint64_t)(a16 + (uint32_t)(ci * TX_PLANE + ky * 32) / 16u),
+                     d_hi | (uint64_t)(w16 + (uint32_t)s * (128u * 32u / 16u)), p.idesc, s > 0 ? 1u : 0u);
+          }
+          umma_commit(&sync->a_empty[b]);
+          umma_commit(&sync->t_full[acc]);
         }
-        umma_commit(&sync->a_empty[b]);
-        umma_commit(&sync->t_full[acc]);
+        __syncwarp();
+        if (++b == TX_ABUF) { b = 0; ph ^= 1u; }
+        if (++acc == TX_ACC) { acc = 0; aph ^= 1u; }            // acc = 2 * (pair parity) + sub
       }
-      __syncwarp();
-      if (++b == TX_ABUF) { b = 0; ph ^= 1u; }
     }
   } else if (warp >= TX_W_EPI) {
-    // ================================================================= epilogue: two groups, alternate tiles
+    // ================================================================= epilogue: group g takes sub-tile g of every pair
+    static_assert(TX_ACC == 4, "accumulator index == 2 * (pair parity) + sub-tile index");
     const int q = warp & 3, grp = (warp - TX_W_EPI) >> 2;
     const int r = q * 32 + lane;                            // TMEM lane = image row of the tile
-    for (int i = grp, t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += 2 * gridDim.x, i += 2) {
-      const int acc = i % TX_ACC;
-      const TxTile c = tx_decode(p, t);
-      const int y = c.y0 + r;
-      const bool valid = y < p.H;
-      uint16_t* yp = p.y + (((size_t)c.n * p.H + y) * p.W + c.x0) * 16;
-      mbar_wait(&sync->t_full[acc], (uint32_t)(i / TX_ACC) & 1u);
-      tc_fence_after();
+    uint8_t* stg = stage + grp * STG * TX_STAGE;
+    const uint32_t srow = (uint32_t)r * 128u;
+    const uint32_t sx = (uint32_t)(r & 7);                  // SWIZZLE_128B: 16-byte chunk j of row r sits at j ^ (r & 7)
+    const bool issuer = (q == 0 && lane == 0);
+    uint32_t tph = 0, odd = 0;
+    for (int pr = blockIdx.x; pr < p.total_pairs; pr += gridDim.x) {
+      const TxTile c = tx_decode(p, pr);
+      const int x0 = c.x0 + grp * TX_COLS;
+      const int acc = grp + 2 * (int)odd;
       const uint32_t t_addr = tmem_base + (uint32_t)acc * 128u + ((uint32_t)(q * 32) << 16);
+      mbar_wait(&sync->t_full[acc], tph);
+      tph ^= odd;
+      odd ^= 1u;
+      tc_fence_after();
 #pragma unroll
-      for (int xo = 0; xo < TX_COLS; ++xo) {
-        uint32_t v[16];
-        tmem_ld16(t_addr + (uint32_t)(xo * 16), v);
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[64];
+        tmem_ld32(t_addr + (uint32_t)(half * 64), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld32(t_addr + (uint32_t)(half * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_ld_wait();
-        if (valid && c.x0 + xo < p.W) {
-          uint32_t w[8];
+        if (half == 1) {                                    // accumulator fully read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sync->t_empty[acc]);
+        }
+        uint4 o[8];
+        if (p.dbg & 16) {
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 sc = *reinterpret_cast<const float4*>(&sync->scale[4 * e4]);
-            const float4 sh = *reinterpret_cast<const float4*>(&sync->shift[4 * e4]);
-            const float a0 = fmaxf(fmaf(__uint_as_float(v[4 * e4]), sc.x, sh.x), 0.f);
-            const float a1 = fmaxf(fmaf(__uint_as_float(v[4 * e4 + 1]), sc.y, sh.y), 0.f);
-            const float a2 = fmaxf(fmaf(__uint_as_float(v[4 * e4 + 2]), sc.z, sh.z), 0.f);
-            const float a3 = fmaxf(fmaf(__uint_as_float(v[4 * e4 + 3]), sc.w, sh.w), 0.f);
-            w[2 * e4] = pack2<DT>(a0, a1);
-            w[2 * e4 + 1] = pack2<DT>(a2, a3);
-          }
-          uint4* o = reinterpret_cast<uint4*>(yp + xo * 16);
-          o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-          o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          for (int j = 0; j < 8; ++j) o[j] = make_uint4(v[8 * j], v[8 * j + 1], v[8 * j + 2] ^ v[8 * j + 4], v[8 * j + 3] ^ v[8 * j + 5] ^ v[8 * j + 6] ^ v[8 * j + 7]);
+        } else {
+#pragma unroll
+        for (int xh = 0; xh < 4; ++xh) tx_bn_pack<DT>(&v[16 * xh], sync, o[2 * xh], o[2 * xh + 1]);
+        }
+        // the TMA store that last read this staging buffer has finished reading it
+        if (issuer) bulk_wait_group_read<STG - 1>();
+        named_bar_sync(1 + grp, 128);
+        uint8_t* sb = stg + (STG == 2 ? half * TX_STAGE : 0) + srow;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(p.dbg & 32) || o[j].x == 0x12345678u) *reinterpret_cast<uint4*>(sb + (((uint32_t)j ^ sx) << 4)) = o[j];
+        if (!(p.dbg & 8)) fence_proxy_async_smem();
+        named_bar_sync(1 + grp, 128);
+        if (issuer) {
+          // tensor {16W, H, N, 1} 16-bit; box {64, 128, 1, 1}: rows below the image and pixels right of it are clipped
+          if (x0 + 4 * half < p.W && !(p.dbg & 1))
+            tma_store_4d(&tmap_y, stg + (STG == 2 ? half * TX_STAGE : 0), (x0 + 4 * half) * 16, c.y0, c.n, 0);
+          bulk_commit_group();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sync->t_empty[acc]);
     }
+    if (issuer) bulk_wait_group<0>();
   } else {
-    // ================================================================= convert: fp32 halo -> 16-bit SWIZZLE_32B halo
-    // work item = (plane ci, halo row hr, 16-byte chunk c): 8 floats -> 8 x 16-bit
+    // ================================================================= convert: input halo -> 16-bit SWIZZLE_32B halo
+    // work item = (plane ci, halo row hr, 16-byte chunk c): 8 pixels of one channel -> 8 x 16-bit
     int b = 0, fb = 0;
     uint32_t ph = 0, fph = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int pr = blockIdx.x; pr < p.total_pairs; pr += gridDim.x) {
+      const TxTile tc = tx_decode(p, pr);
       mbar_wait(&sync->f_full[fb], fph);
-      mbar_wait(&sync->a_empty[b], ph ^ 1u);
-      const float* f = reinterpret_cast<const float*>(fbuf + fb * F_STRIDE);
-      uint8_t* a = abuf + b * ((TX_A_BYTES + 1023) & ~1023);
-      for (int it = tid; it < 3 * TX_HROWS * 2; it += TX_CVT_WARPS * 32) {
-        const int c = it & 1, hr = (it >> 1) % TX_HROWS, ci = (it >> 1) / TX_HROWS;
-        const float4* src = reinterpret_cast<const float4*>(f + (ci * TX_HROWS + hr) * TX_HW + c * 8);
-        const float4 u = src[0], v = src[1];
-        *reinterpret_cast<uint4*>(a + ci * TX_PLANE + swz_offset((uint32_t)hr, (uint32_t)c, 32)) =
-            make_uint4(pack2<DT>(u.x, u.y), pack2<DT>(u.z, u.w), pack2<DT>(v.x, v.y), pack2<DT>(v.z, v.w));
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        mbar_wait(&sync->a_empty[b], ph ^ 1u);
+        uint8_t* a = abuf + b * TX_A_STRIDE;
+        if (SRC == SRC_F32) {
+          const float* f = reinterpret_cast<const float*>(fbuf + fb * F_STRIDE) + sub * TX_COLS;
+          for (int it = tid; it < ((p.dbg & 2) ? 0 : 3 * TX_HROWS * 2); it += TX_CVT_WARPS * 32) {
+            const int c = it & 1, hr = (it >> 1) % TX_HROWS, ci = (it >> 1) / TX_HROWS;
+            const float4* src = reinterpret_cast<const float4*>(f + (ci * TX_HROWS + hr) * TX_PW + c * 8);
+            const float4 u = src[0], v = src[1];
+            *reinterpret_cast<uint4*>(a + ci * TX_PLANE + swz_offset((uint32_t)hr, (uint32_t)c, 32)) =
+                make_uint4(pack2<DT>(u.x, u.y), pack2<DT>(u.z, u.w), pack2<DT>(v.x, v.y), pack2<DT>(v.z, v.w));
+          }
+        } else {
+          const uint8_t* f = fbuf + fb * F_STRIDE + 4 + sub * (TX_COLS * 3);
+          for (int it = tid; it < ((p.dbg & 2) ? 0 : 3 * TX_HROWS * 2); it += TX_CVT_WARPS * 32) {
+            const int c = it & 1, hr = (it >> 1) % TX_HROWS, ci = (it >> 1) / TX_HROWS;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(f + hr * TX_U8_ROW + c * 24);
+            uint32_t wd[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) wd[k] = src[k];
+            const bool rowok = (unsigned)(tc.y0 - 3 + hr) < (unsigned)p.H;
+            const int xb = tc.x0 + sub * TX_COLS - 4 + c * 8;
+            const uint16_t* lut = sync->lut + ci * 256;
+            const int ch = p.bgr ? 2 - ci : ci;
+            uint4 o;
+            if (ch == 0) o = tx_u8_lookup<0>(wd, lut, xb, p.W, rowok);
+            else if (ch == 1) o = tx_u8_lookup<1>(wd, lut, xb, p.W, rowok);
+            else o = tx_u8_lookup<2>(wd, lut, xb, p.W, rowok);
+            *reinterpret_cast<uint4*>(a + ci * TX_PLANE + swz_offset((uint32_t)hr, (uint32_t)c, 32)) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sync->a_full[b]);
+          if (sub == 1) mbar_arrive(&sync->f_empty[fb]);
+        }
+        if (++b == TX_ABUF) { b = 0; ph ^= 1u; }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&sync->a_full[b]);
-        mbar_arrive(&sync->f_empty[fb]);
-      }
-      if (++b == TX_ABUF) { b = 0; ph ^= 1u; }
       if (++fb == TX_RING) { fb = 0; fph ^= 1u; }
     }
   }
@@ -268,7 +393,9 @@ struct StemTxState {
   int32_t *d_row_ptr = nullptr, *d_kblk = nullptr;
   uint16_t* d_wpacked = nullptr;
   const void* map_ptr = nullptr;
-  CUtensorMap map;
+  const void* map_y_ptr = nullptr;
+  int map_kind = -1;
+  CUtensorMap map, map_y;
 };
 
 int stem_tx_create(StemTxState** out, const float* w_oihw, int act_dtype, cudaStream_t st) {
@@ -293,54 +420,83 @@ void stem_tx_destroy(StemTxState* s) {
   delete s;
 }
 
-int stem_tx_forward(StemTxState* s, const float* x, void* y, const float* scale, const float* shift, int N,
-                    int H, int W, int act_dtype, cudaStream_t st) {
+int stem_tx_forward(StemTxState* s, const void* x, int src_kind, const uint16_t* lut, int bgr, void* y,
+                    const float* scale, const float* shift, int N, int H, int W, int act_dtype, cudaStream_t st) {
   StemTxParams p{};
-  p.x = x; p.y = reinterpret_cast<uint16_t*>(y); p.w_packed = reinterpret_cast<const uint8_t*>(s->d_wpacked);
+  p.lut = lut; p.bgr = bgr; p.w_packed = reinterpret_cast<const uint8_t*>(s->d_wpacked);
   p.scale = scale; p.shift = shift; p.N = N; p.H = H; p.W = W;
-  p.tiles_x = (W + TX_COLS - 1) / TX_COLS;
+  p.pairs_x = (W + 2 * TX_COLS - 1) / (2 * TX_COLS);
   p.tiles_y = (H + TX_ROWS - 1) / TX_ROWS;
-  p.total_tiles = N * p.tiles_x * p.tiles_y;
-  if ((uint64_t)p.total_tiles * (uint64_t)std::max(p.tiles_x, p.tiles_y) >= (1ull << 32)) {
+  p.total_pairs = N * p.pairs_x * p.tiles_y;
+  if ((uint64_t)p.total_pairs * (uint64_t)std::max(p.pairs_x, p.tiles_y) >= (1ull << 32)) {
     set_error("stem_tx: problem too large for the 32-bit tile decode");
     return DRNB200_E_ARG;
   }
-  p.magic_x = p.tiles_x == 1 ? 0u : (uint32_t)(((1ull << 32) + p.tiles_x - 1) / p.tiles_x);
+  if (src_kind == SRC_U8 && (W % 16 != 0 || lut == nullptr)) {
+    set_error("stem_tx: the uint8 ingest needs W %% 16 == 0 (TMA row pitch) and a table (W=%d)", W);
+    return DRNB200_E_ARG;
+  }
+  p.magic_x = p.pairs_x == 1 ? 0u : (uint32_t)(((1ull << 32) + p.pairs_x - 1) / p.pairs_x);
   p.magic_y = p.tiles_y == 1 ? 0u : (uint32_t)(((1ull << 32) + p.tiles_y - 1) / p.tiles_y);
   p.idesc = umma_idesc_f16(128, 128, act_dtype);
-  if (s->map_ptr != x) {
-    auto fn = tx_encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return DRNB200_E_CUDA; }
-    cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)N};
-    cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * 12};
-    cuuint32_t box[4] = {(cuuint32_t)TX_HW, (cuuint32_t)TX_HROWS, 3, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(&s->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  static const char* envd = getenv("DRNB200_DBG");
+  p.dbg = envd ? atoi(envd) : 0;
+  auto fn = tx_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return DRNB200_E_CUDA; }
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (s->map_ptr != x || s->map_kind != src_kind) {
+    CUresult r;
+    if (src_kind == SRC_F32) {
+      cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)N};
+      cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * 12};
+      cuuint32_t box[4] = {(cuuint32_t)TX_PW, (cuuint32_t)TX_HROWS, 3, 1};
+      r = fn(&s->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t gdim[4] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)N, 1};
+      cuuint64_t gstr[3] = {(cuuint64_t)W * 3, (cuuint64_t)W * H * 3, (cuuint64_t)W * H * 3 * N};
+      cuuint32_t box[4] = {(cuuint32_t)TX_U8_ROW, (cuuint32_t)TX_HROWS, 1, 1};
+      r = fn(&s->map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled(stem_tx) failed with CUresult %d (W=%d H=%d N=%d)", (int)r, W, H, N);
+      set_error("cuTensorMapEncodeTiled(stem_tx in, kind %d) failed with CUresult %d (W=%d H=%d N=%d)", src_kind,
+                (int)r, W, H, N);
       return DRNB200_E_CUDA;
     }
-    s->map_ptr = x;
+    s->map_ptr = x; s->map_kind = src_kind;
   }
-  constexpr int F_STRIDE = (TX_F_BYTES + 127) & ~127;
-  const size_t smem = 1024 + TX_ABUF * ((TX_A_BYTES + 1023) & ~1023) + TX_B_BYTES + TX_RING * F_STRIDE + sizeof(TxSync);
-  static bool attr[2] = {false, false};
-  if (!attr[act_dtype]) {
-    if (act_dtype == DRNB200_BF16)
-      DRN_CUDA(cudaFuncSetAttribute(stem_tx_kernel<DRNB200_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-      DRN_CUDA(cudaFuncSetAttribute(stem_tx_kernel<DRNB200_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[act_dtype] = true;
+  if (s->map_y_ptr != y) {
+    cuuint64_t gdim[4] = {(cuuint64_t)W * 16, (cuuint64_t)H, (cuuint64_t)N, 1};
+    cuuint64_t gstr[3] = {(cuuint64_t)W * 32, (cuuint64_t)W * H * 32, (cuuint64_t)W * H * 32 * N};
+    cuuint32_t box[4] = {64, (cuuint32_t)TX_ROWS, 1, 1};
+    CUresult r = fn(&s->map_y, act_dtype == DRNB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                    4, y, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(stem_tx out) failed with CUresult %d (W=%d H=%d N=%d)", (int)r, W, H, N);
+      return DRNB200_E_CUDA;
+    }
+    s->map_y_ptr = y;
+  }
+  const size_t smem = tx_smem_bytes(src_kind);
+  void (*kern)(const CUtensorMap, const CUtensorMap, const StemTxParams) =
+      act_dtype == DRNB200_BF16
+          ? (src_kind == SRC_U8 ? stem_tx_kernel<DRNB200_BF16, SRC_U8> : stem_tx_kernel<DRNB200_BF16, SRC_F32>)
+          : (src_kind == SRC_U8 ? stem_tx_kernel<DRNB200_F16, SRC_U8> : stem_tx_kernel<DRNB200_F16, SRC_F32>);
+  static bool attr[2][2] = {{false, false}, {false, false}};
+  if (!attr[act_dtype][src_kind]) {
+    DRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[act_dtype][src_kind] = true;
   }
   int dev = 0, sms = 148;
   DRN_CUDA(cudaGetDevice(&dev));
   DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = std::min(p.total_tiles, sms);
+  const int grid = std::min(p.total_pairs, sms);
   if (grid == 0) return DRNB200_OK;
-  if (act_dtype == DRNB200_BF16) stem_tx_kernel<DRNB200_BF16><<<grid, TX_THREADS, smem, st>>>(s->map, p);
-  else stem_tx_kernel<DRNB200_F16><<<grid, TX_THREADS, smem, st>>>(s->map, p);
+  kern<<<grid, TX_THREADS, smem, st>>>(s->map, s->map_y, p);
   DRN_CUDA(cudaGetLastError());
   return DRNB200_OK;
 }

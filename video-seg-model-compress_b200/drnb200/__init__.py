@@ -8,6 +8,10 @@ from .model import DRNSeg, fill_up_weights
 from . import drn
 from . import pruners
 from .evalops import ConfusionMeter, fast_hist, per_class_iu, shard_frames
+from .engine import ingest_lut
+from . import frameio
+from .frameio import CITYSCAPE_PALETTE, colorize, overlay, load_info
 
 __all__ = ["DRNSeg", "fill_up_weights", "drn", "pruners", "ffi", "ConfusionMeter", "fast_hist",
-           "per_class_iu", "shard_frames"]
+           "per_class_iu", "shard_frames", "frameio", "CITYSCAPE_PALETTE", "colorize", "overlay", "load_info",
+           "ingest_lut"]

@@ -262,6 +262,16 @@ class _Timed:
         return False
 
 
+def ingest_lut(mean, std, act_dtype):
+    """[3,256] int16 table of act_dtype bit patterns: ((b / 255) - mean[c]) / std[c] in correctly rounded fp32
+    steps (the reference's torch CPU transforms), then one rounding to act_dtype.  Host function of the C ABI."""
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    sd = (C.c_float * 3)(*[float(v) for v in std])
+    out = torch.empty((3, 256), dtype=torch.int16)
+    ffi.check(ffi.lib().drnb200_ingest_lut(m, sd, int(act_dtype), out.data_ptr()), "ingest_lut")
+    return out
+
+
 class Engine:
     """builds and runs the launch list for one DRNSeg module"""
 
@@ -276,6 +286,8 @@ class Engine:
         self.head_plans = {}
         self.head_version = None
         self.stem_plans = {}
+        self.ingest = None     # (mean, std, bgr) for uint8 frames
+        self._lut = None
         self.stem_impl = "tcgen05"   # or "direct": CUDA-core fp32 stem (no input rounding), cross-check
         self.launches_per_forward = 0
         self._build_graph()
@@ -406,6 +418,17 @@ class Engine:
             self.head_version = hver
         return rebuilt
 
+    def set_ingest(self, mean, std, bgr=False):
+        """normalisation of uint8 frames (data_transforms.py:109-125: (x/255 - mean) / std per channel)"""
+        self.ingest = (tuple(float(m) for m in mean), tuple(float(v) for v in std), bool(bgr))
+        self._lut = None
+
+    def _ingest_lut(self, device):
+        if self._lut is None or self._lut[0] != (device, self.act_dtype):
+            self._lut = ((device, self.act_dtype),
+                         ingest_lut(self.ingest[0], self.ingest[1], self.act_dtype).to(device))
+        return self._lut[1]
+
     def _drop_stem_plans(self):
         lib = ffi.lib()
         for p in self.stem_plans.values():
@@ -465,10 +488,24 @@ class Engine:
         def timed(name):
             return _Timed(name, timings)
 
-        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3):
-            raise ffi.Drnb200Error("input must be a float32 CUDA tensor [N,3,H,W] (got %s %s on %s); "
-                                   "there is no CPU path" % (tuple(x.shape), x.dtype, x.device))
-        N, _, H, W = x.shape
+        u8 = x.dtype == torch.uint8
+        if u8:
+            # frame ingest fused into the stem: uint8 HWC frames (cv2 / PIL order), normalisation via set_ingest()
+            if not (x.is_cuda and x.dim() == 4 and x.shape[3] == 3):
+                raise ffi.Drnb200Error("uint8 input must be a CUDA tensor [N,H,W,3] (got %s on %s); "
+                                       "there is no CPU path" % (tuple(x.shape), x.device))
+            if self.ingest is None:
+                raise ffi.Drnb200Error("uint8 frames need set_ingest(mean, std) first (info.json of the dataset)")
+            if self.stem_impl == "direct":
+                raise ffi.Drnb200Error("the CUDA-core stem has no uint8 ingest")
+            N, H, W, _ = x.shape
+            if W % 16:
+                raise ffi.Drnb200Error("uint8 ingest needs W %% 16 == 0 (got %d)" % W)
+        else:
+            if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3):
+                raise ffi.Drnb200Error("input must be a float32 CUDA tensor [N,3,H,W] (got %s %s on %s); "
+                                       "there is no CPU path" % (tuple(x.shape), x.dtype, x.device))
+            N, _, H, W = x.shape
         if H % 8 or W % 8:
             raise ffi.Drnb200Error("H and W must be multiples of 8 (got %dx%d)" % (H, W))
         x = x.contiguous()
@@ -510,6 +547,10 @@ class Engine:
                 ffi.check(lib.drnb200_stem_forward(ffi.ptr(x), ffi.ptr(self.stem_w), ffi.ptr(self.stem_scale),
                                                    ffi.ptr(self.stem_shift), N, H, W, c0, adt, ffi.ptr(y), st),
                           "stem_forward")
+            elif u8:
+                ffi.check(lib.drnb200_stem_plan_forward_u8(self._stem_plan(N, H, W), ffi.ptr(x),
+                                                           ffi.ptr(self._ingest_lut(dev)), int(self.ingest[2]),
+                                                           ffi.ptr(y), st), "stem_plan_forward_u8")
             else:
                 ffi.check(lib.drnb200_stem_plan_forward(self._stem_plan(N, H, W), ffi.ptr(x), ffi.ptr(y), st),
                           "stem_plan_forward")

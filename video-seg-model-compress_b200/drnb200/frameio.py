@@ -1,0 +1,70 @@
+"""Steps either side of the hot path in the reference's video caller, on the device:
+
+* ingest: uint8 HWC frames go straight into `DRNSeg.predict` / `forward` after `DRNSeg.set_ingest(mean, std)`
+  (the normalisation is fused into the stem kernel); `load_info()` reads the reference's `info.json`.
+* `colorize(labels)` = `CITYSCAPE_PALETTE[pred]` (semantic_seg.py:52-72, :101-112), `overlay(labels, frames)` =
+  the alpha=0.6 blend over the frame that seg_video.py:200-203 draws.
+"""
+import json
+
+import numpy as np
+import torch
+
+from . import ffi
+
+# the Cityscapes train-id colours (semantic_seg.py:52-72); row 19 (black) is used for the ignore label
+CITYSCAPE_PALETTE = np.asarray([
+    [128, 64, 128], [244, 35, 232], [70, 70, 70], [102, 102, 156], [190, 153, 153], [153, 153, 153],
+    [250, 170, 30], [220, 220, 0], [107, 142, 35], [152, 251, 152], [70, 130, 180], [220, 20, 60], [255, 0, 0],
+    [0, 0, 142], [0, 0, 70], [0, 60, 100], [0, 80, 100], [0, 0, 230], [119, 11, 32], [0, 0, 0]], dtype=np.uint8)
+
+
+def load_info(path):
+    """(mean, std) from the reference's info.json (`{"mean": [...], "std": [...]}`)"""
+    with open(path) as fh:
+        info = json.load(fh)
+    return tuple(info["mean"]), tuple(info["std"])
+
+
+_pal_cache = {}
+
+
+def _device_palette(palette, device):
+    pal = np.ascontiguousarray(np.asarray(palette, dtype=np.uint8))
+    if pal.ndim != 2 or pal.shape[1] != 3 or not (1 <= pal.shape[0] <= 256):
+        raise ffi.Drnb200Error("palette must be uint8 [n_colors<=256, 3] (got %s)" % (pal.shape,))
+    key = (pal.tobytes(), str(device))
+    t = _pal_cache.get(key)
+    if t is None:
+        t = _pal_cache[key] = torch.from_numpy(pal).to(device)
+    return t
+
+
+def _colorize(labels, frames, alpha, palette):
+    if not (labels.is_cuda and labels.dtype == torch.uint8):
+        raise ffi.Drnb200Error("labels must be a uint8 CUDA tensor (got %s on %s); there is no CPU path"
+                               % (labels.dtype, labels.device))
+    labels = labels.contiguous()
+    if labels.numel() % 4:
+        raise ffi.Drnb200Error("the pixel count must be a multiple of 4")
+    if frames is not None:
+        if not (frames.is_cuda and frames.dtype == torch.uint8 and tuple(frames.shape) == tuple(labels.shape) + (3,)):
+            raise ffi.Drnb200Error("frames must be a uint8 CUDA tensor of shape labels.shape + (3,)")
+        frames = frames.contiguous()
+    pal = _device_palette(palette, labels.device)
+    out = torch.empty(tuple(labels.shape) + (3,), dtype=torch.uint8, device=labels.device)
+    if labels.numel() == 0:
+        return out
+    ffi.check(ffi.lib().drnb200_colorize(ffi.ptr(labels), labels.numel(), ffi.ptr(pal), pal.shape[0],
+                                         ffi.ptr(frames), float(alpha), ffi.ptr(out), ffi.stream_ptr()), "colorize")
+    return out
+
+
+def colorize(labels, palette=CITYSCAPE_PALETTE):
+    """uint8 labels [..., H, W] -> uint8 RGB [..., H, W, 3]"""
+    return _colorize(labels, None, 0.0, palette)
+
+
+def overlay(labels, frames, alpha=0.6, palette=CITYSCAPE_PALETTE):
+    """rint(alpha * palette[labels] + (1 - alpha) * frames), uint8 RGB"""
+    return _colorize(labels, frames, alpha, palette)

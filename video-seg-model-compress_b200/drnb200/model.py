@@ -66,6 +66,7 @@ class DRNSeg(nn.Module):
         self._act_dtype = act_dtype
         self._engine = None
         self._mask_dict = None
+        self._ingest = None
 
     # ---- reference API ---------------------------------------------------------------------------
     def forward(self, x):
@@ -84,6 +85,14 @@ class DRNSeg(nn.Module):
         """uint8 label map [N,H,W] == torch.max(model(x)[0], 1)[1] of the reference, without ever
         writing the [N,classes,H,W] logits."""
         return self._eng().run(x, want_labels=True)[0]
+
+    def set_ingest(self, mean, std, bgr=False):
+        """enable uint8 HWC frames [N,H,W,3] as input of forward()/predict(): ToTensorVideoImage + Normalize
+        (data_transforms.py:109-125, :256-281; mean/std from info.json) are fused into the stem kernel."""
+        self._ingest = (mean, std, bgr)
+        if self._engine is not None:
+            self._engine.set_ingest(mean, std, bgr)
+        return self
 
     def set_masks(self, mask_dict):
         self._mask_dict = mask_dict
@@ -121,6 +130,8 @@ class DRNSeg(nn.Module):
             ffi.lib()                      # fail loudly if the CUDA library is missing
             self._engine = Engine(self, act_dtype=self._act_dtype)
             self._engine.set_masks(self._mask_dict)
+            if self._ingest is not None:
+                self._engine.set_ingest(*self._ingest)
         return self._engine
 
     def __del__(self):
