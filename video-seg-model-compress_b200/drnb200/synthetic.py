@@ -83,6 +83,23 @@ def make_frames(n, h, w, seed=1234):
     return torch.randn(n, 3, h, w, generator=torch.Generator().manual_seed(seed))
 
 
+def make_u8_frames(n, h, w, seed=1234, noise=16):
+    """video-like uint8 HWC frames [N,H,W,3]: a smooth low-frequency field per channel plus +-`noise` of
+    per-pixel noise (camera frames are spatially coherent; pure random bytes are the worst case for the
+    ingest table's shared-memory lookups and are used in the tests instead)"""
+    g = torch.Generator().manual_seed(seed)
+    yy = torch.linspace(0, 1, h).view(1, h, 1, 1)
+    xx = torch.linspace(0, 1, w).view(1, 1, w, 1)
+    ph = torch.rand(n, 1, 1, 3, generator=g) * 6.28
+    fr = 2.0 + 6.0 * torch.rand(n, 1, 1, 3, generator=g)
+    base = 128 + 70 * torch.sin(fr * xx * 3.1 + ph) * torch.cos(fr * yy * 2.3 - ph) + 30 * (xx - yy)
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8)
+    for i in range(n):                      # per frame: keeps the float temporaries small
+        nz = torch.randint(-noise, noise + 1, (h, w, 3), generator=g).float()
+        out[i] = (base[i] + nz).clamp_(0, 255).to(torch.uint8)
+    return out
+
+
 def prunable_keys(shapes):
     """conv weights the reference's experiment configs prune: everything except the 7x7 stem and `seg`
     (expander_batch.py:42-43; optimal_configs/drn_d_22/* list exactly these 24 layers for D-22)"""
