@@ -312,7 +312,7 @@ def main():
         layers = []
         lib = drnb200.ffi.lib()
         KERNELS = {0: "conv_tc<T>", 1: "conv_tc<P>", 2: "conv_tc<T,f32>", 3: "conv_gather", 4: "conv_halo",
-                   -1: "conv_direct"}
+                   5: "conv_tc<T,ROW>", -1: "conv_direct"}
         shapes = {-1: (H, W)}
         for i, op in enumerate(eng.ops):
             src = op.input_from if op.input_from is not None else i - 1
@@ -328,8 +328,13 @@ def main():
                            "tensor_frac": 2 * macs / (lms * 1e-3) / 1e12 / pk["tflops"],
                            "hbm_gbs": io_bytes / (lms * 1e-3) / 1e9,
                            "live_tiles": op.n_live, "tile": [op.tile_o, op.tile_ci]})
-        # the dominant kernel: conv_tc_kernel<MODE_T> (layers 4-8), aggregated over its launches of one step
-        dom = [l for l in layers if l["kernel"] == "conv_tc<T>"]
+        # the dominant kernel = the one with the largest share of the step (conv_tc_kernel<MODE_T, ROW>: the 3x3
+        # stride-1 convs of layers 4-8), aggregated over its launches of one step
+        by_kernel = collections.defaultdict(float)
+        for l in layers:
+            by_kernel[l["kernel"]] += l["ms"]
+        dom_name = max(by_kernel, key=by_kernel.get)
+        dom = [l for l in layers if l["kernel"] == dom_name]
         dom_ms = sum(l["ms"] for l in dom)
         dom_tflops = 2.0 * sum(l["live_gmac"] for l in dom) * 1e9 / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
         if args.layers_out:
@@ -349,7 +354,8 @@ def main():
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor",
-                         "kernel": "conv_tc_kernel<MODE_T> (%d launches per step: layers 4-8)" % len(dom),
+                         "kernel": "%s (%d launches per step: %s)" % (
+                             dom_name, len(dom), ", ".join(l["layer"].replace("layer.", "") for l in dom)),
                          "achieved": dom_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": dom_tflops / pk["tflops"], "traffic": None,
                          "peak_source": pk["src"] + " bf16_tflops_sustained",

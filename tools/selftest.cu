@@ -393,6 +393,11 @@ static const ConvCase kCases[] = {
     {"tcT_ci32",           1, 16, 32, 32, 128, 3, 1, 1, 1, 0, 0, 0, 128, 32, 2, 1.0f, 0, 0, 0},
     {"tcT_big_sparse",     2, 64,128, 512,512, 3, 1, 4, 1, 1, 0, 0, 128, 64, 2, 0.25f,0, 0, 1},
     {"tcT_big_dense",      2, 64,128, 256,512, 3, 1, 2, 1, 0, 0, 0, 128, 64, 2, 1.0f, 0, 0, 1},
+    // ROW variant (rows of >= 256 output pixels): halo shifts for dil 1/2/4, ragged right edge, per-tap sparsity
+    {"tcR_d1",             1,  6,260, 64, 128, 3, 1, 1, 1, 0, 0, 0, 128, 64, 2, 1.0f, 0, 0, 0},
+    {"tcR_d2_res",         2,  5,300, 128,256, 3, 1, 2, 1, 1, 1, 0, 128, 64, 2, 1.0f, 0, 0, 0},
+    {"tcR_d4_pertap",      1,  9,520, 128,128, 3, 1, 4, 1, 1, 0, 0, 128, 64, 2, 0.5f, 1, 0, 0},
+    {"tcR_d4_sparse",      1,  7,256, 256,256, 3, 1, 4, 0, 0, 1, 0, 128, 64, 2, 0.3f, 0, 0, 0},
     {"tcP_16_16",          1, 16, 32, 16,  16, 3, 1, 1, 1, 0, 0, 0,  16, 16, 2, 1.0f, 0, 0, 0},
     {"tcH_d2",             1, 20, 24, 64,  64, 3, 1, 2, 1, 0, 0, 0,  64, 64, 2, 1.0f, 0, 0, 0},
     {"tcH_32_d4",          2, 17, 19, 32,  32, 3, 1, 4, 1, 1, 1, 0,  32, 32, 2, 1.0f, 0, 0, 0},

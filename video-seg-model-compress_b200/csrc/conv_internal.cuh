@@ -32,6 +32,9 @@ struct ConvParams {
   uint32_t w_tile_bytes, x_tile_bytes, w_stage_bytes, stage_bytes, pitch;
   // ---- staged epilogue (MODE_T, 16-bit output): 32-pixel x 128-cout chunks through shared memory + TMA
   int ep_cw, ep_ch, ep_nch;   // chunk box (pixels wide x high), chunks per tile
+  // ---- ROW variant of MODE_T (conv_tc.cu): input-row halo ring + weight-tile ring
+  int row_mode, x_ring, w_ring, dbg;
+  uint32_t main_bytes;
 };
 
 }  // namespace drnb200
@@ -47,6 +50,7 @@ struct drnb200_conv_plan {
   int32_t* d_ot_order;
   CUtensorMap tmap;        // activations, bound to `tmap_ptr`
   const void* tmap_ptr;
+  CUtensorMap tmap_x2;     // ROW variant: the 8 halo pixels right of the row box (same tensor as `tmap`)
   CUtensorMap tmap_y, tmap_r;   // output / residual chunk boxes (staged epilogue), bound to the pointers below
   const void* tmap_y_ptr;
   const void* tmap_r_ptr;

@@ -110,7 +110,8 @@ extern "C" int drnb200_conv_forward(drnb200_conv_plan* plan, const void* x_nhwc,
 extern "C" int drnb200_conv_plan_impl(const drnb200_conv_plan* plan) { return plan ? plan->impl : 0; }
 
 extern "C" int drnb200_conv_plan_mode(const drnb200_conv_plan* plan) {
-  return (plan && plan->impl == DRNB200_IMPL_TCGEN05) ? plan->tc_mode : -1;
+  if (!plan || plan->impl != DRNB200_IMPL_TCGEN05) return -1;
+  return (plan->tc_mode == 0 && plan->p.row_mode) ? 5 : plan->tc_mode;
 }
 
 extern "C" int64_t drnb200_conv_plan_tile_macs(const drnb200_conv_plan* plan) {

@@ -22,8 +22,17 @@
 // the residual chunk arrives there by TMA (prefetched one chunk ahead), every thread fuses
 // BN affine + residual + ReLU in place (2-byte accesses, 64 contiguous bytes per warp: conflict-free),
 // and one TMA store per chunk writes full 256-byte pixel rows (out-of-image pixels are clipped by TMA).
+//
+// ROW variant of MODE_T (3x3, stride 1, 64-channel K-blocks, rows of >= 256 output pixels).  Measured on B200: the
+// plain K-block pipeline is bound by L2 -> SM bandwidth (48 KB per K-block against ~45 B/clk/SM, i.e. ~1000 cycles
+// for 512 cycles of MMA).  The three taps (ky, kx = 0..2) of a filter row read the SAME input row shifted by
+// kx*dil pixels, so the row is loaded once as a halo [256 + 2*dil pixels][64 ch] (SWIZZLE_128B) and each tap's B
+// operand is the UMMA descriptor started kx*dil pixel rows further (the UMMA swizzle uses absolute shared-memory
+// address bits, conv_halo.cu).  Activation traffic drops from 9 x 32 KB to 3 x 33 KB per 64-channel block; rows and
+// weight tiles travel through two independent rings (X: 33 KB slots, W: 16 KB slots).
 #include "conv_internal.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cudaTypedefs.h>
 
 namespace drnb200 {
@@ -37,12 +46,19 @@ constexpr uint32_t kTmemCols = 512;
 constexpr int kEpRing = 4;     // staging buffers of the MODE_T epilogue
 constexpr int kEpChunkPx = 32; // pixels per staged chunk (one tcgen05.ld.32x32b.x32 per warp)
 constexpr int kEpBufBytes = kEpChunkPx * 256;
+constexpr int kRowPx = 256;                       // ROW variant: output pixels per tile (one row segment)
+constexpr int kRowHaloPx = kRowPx + 8;            // + 2*dil (dil <= 4) halo pixels
+constexpr int kRowBytes = kRowHaloPx * 128;       // one X-ring slot (33 x 1024 B)
+constexpr int kRowWBytes = 128 * 128;             // one W-ring slot: 128 couts x 64 ch x 2 B
+constexpr int kMaxXRing = 4;
 
 struct __align__(16) TcSync {
   alignas(16) float scale[256];   // MODE_P: BN affine of all (<= 256) output channels, read by every pixel thread
   alignas(16) float shift[256];   //         (no L1 is left once the CTA takes ~all shared memory)
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
+  uint64_t xfull[kMaxXRing];  // ROW variant: input-row ring (full/empty above are then the weight-tile ring)
+  uint64_t xempty[kMaxXRing];
   uint64_t tfull[2];
   uint64_t tempty[2];
   uint64_t rfull[kEpRing];    // staged epilogue: residual chunk landed in ring slot (TMA)
@@ -78,15 +94,17 @@ __device__ __forceinline__ float finish(float acc, float sc, float sh, float res
   return relu ? fmaxf(v, 0.f) : v;
 }
 
-template <int MODE, int DT>
+template <int MODE, int DT, bool ROW = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y,
-               const __grid_constant__ CUtensorMap tmap_r, const ConvParams p) {
+               const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_x2,
+               const ConvParams p) {
+  static_assert(!ROW || MODE == MODE_T, "the ROW mainloop feeds the staged MODE_T epilogue");
   extern __shared__ uint8_t smem_raw[];
   // tiles must sit on 1024-byte boundaries of the shared window (SWIZZLE_128B atom)
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* stg = smem + (size_t)p.stages * p.stage_bytes;            // MODE_T staging ring
+  uint8_t* stg = smem + (ROW ? (size_t)p.main_bytes : (size_t)p.stages * p.stage_bytes);   // MODE_T staging ring
   TcSync* sync = reinterpret_cast<TcSync*>(stg + (MODE == MODE_T ? kEpRing * kEpBufBytes : 0));
 
   const int warp = threadIdx.x >> 5;
@@ -103,9 +121,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       mbar_init(&sync->sfree[b], 1);
       mbar_init(&sync->sdone[b], 4);
     }
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < (ROW ? p.w_ring : p.stages); ++s) {
       mbar_init(&sync->full[s], 1);
       mbar_init(&sync->empty[s], 1);
+    }
+    if (ROW) {
+      tma_prefetch_desc(&tmap_x2);
+      for (int s = 0; s < p.x_ring; ++s) {
+        mbar_init(&sync->xfull[s], 1);
+        mbar_init(&sync->xempty[s], 1);
+      }
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sync->tfull[a], 1);
@@ -132,7 +157,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // ===================================================================== TMA producer
     // (the whole warp runs the loop with warp-uniform values, one elected lane issues: inside an
     //  `if (lane == 0)` region nothing is provably uniform and every operand goes through R2UR)
-    {
+    if (ROW) {
+      // entries of the tile list are sorted by kb = cib*9 + ky*3 + kx: a run with equal kb/3 = one input row
+      uint32_t xs = 0, xph = 0, ws = 0, wph = 0;
+      uint8_t* wring = smem + (size_t)p.x_ring * kRowBytes;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        int j = c.jb;
+        int kb = (j < c.je) ? __ldg(p.kblk + j) : 0;
+        while (j < c.je) {
+          const int g = kb / 3, cib = g / 3, ky = g - cib * 3;
+          uint8_t* sX = smem + (size_t)xs * kRowBytes;
+          mbar_wait(&sync->xempty[xs], xph ^ 1u);
+          if (p.dbg & 2) {
+            if (elect_one()) mbar_arrive(&sync->xfull[xs]);
+          } else if (elect_one()) {
+            mbar_arrive_expect_tx(&sync->xfull[xs], kRowBytes);
+            const int x0 = c.ox0 - p.dil, y = c.oy0 + (ky - 1) * p.dil;
+            tma_load_4d(&tmap, &sync->xfull[xs], sX, cib * 64, x0, y, c.n);                        // 256 pixels
+            tma_load_4d(&tmap_x2, &sync->xfull[xs], sX + kRowPx * 128, cib * 64, x0 + kRowPx, y, c.n);   // + 8
+          }
+          __syncwarp();
+          if (++xs == (uint32_t)p.x_ring) { xs = 0; xph ^= 1u; }
+          do {
+            mbar_wait(&sync->empty[ws], wph ^ 1u);
+            if (p.dbg & 1) {
+              if (elect_one()) mbar_arrive(&sync->full[ws]);
+            } else if (elect_one()) {
+              mbar_arrive_expect_tx(&sync->full[ws], kRowWBytes);
+              bulk_load(p.w_packed + (size_t)j * kRowWBytes, &sync->full[ws], wring + (size_t)ws * kRowWBytes,
+                        kRowWBytes);
+            }
+            __syncwarp();
+            if (++ws == (uint32_t)p.w_ring) { ws = 0; wph ^= 1u; }
+            ++j;
+            if (j < c.je) kb = __ldg(p.kblk + j);
+          } while (j < c.je && kb / 3 == g);
+        }
+      }
+    } else {
       uint32_t stage = 0, phase = 0;
       const int half = (p.taps == 9) ? 1 : 0;
       const uint32_t tx_bytes = p.w_tile_bytes + p.x_tile_bytes;
@@ -161,7 +224,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (warp-uniform loop)
-    {
+    if (ROW) {
+      uint32_t xs = 0, xph = 0, ws = 0, wph = 0, acc = 0, acc_phase = 0;
+      const uint64_t d_hi = umma_smem_desc(0u, 128);
+      const uint32_t x16 = smem_u32(smem) >> 4, w16 = x16 + (uint32_t)p.x_ring * (kRowBytes >> 4);
+      const uint32_t shift16 = (uint32_t)p.dil * 8u;          // kx*dil pixel rows of 128 B, in 16-byte units
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        if (c.je == c.jb) continue;
+        mbar_wait(&sync->tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256u;
+        int j = c.jb;
+        int kb = __ldg(p.kblk + j);
+        while (j < c.je) {
+          const int g = kb / 3;
+          mbar_wait(&sync->xfull[xs], xph);
+          const uint32_t sX16 = x16 + xs * (uint32_t)(kRowBytes >> 4);
+          do {
+            const uint32_t kx = (uint32_t)(kb - g * 3);
+            mbar_wait(&sync->full[ws], wph);
+            tc_fence_after();
+            const uint32_t sW16 = w16 + ws * (uint32_t)(kRowWBytes >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                umma_f16(d_tmem, d_hi | (uint64_t)(sW16 + 2u * i), d_hi | (uint64_t)(sX16 + kx * shift16 + 2u * i),
+                         p.idesc, (j > c.jb || i > 0) ? 1u : 0u);
+              umma_commit(&sync->empty[ws]);
+            }
+            __syncwarp();
+            if (++ws == (uint32_t)p.w_ring) { ws = 0; wph ^= 1u; }
+            ++j;
+            if (j < c.je) kb = __ldg(p.kblk + j);
+          } while (j < c.je && kb / 3 == g);
+          if (elect_one()) umma_commit(&sync->xempty[xs]);      // the row's taps have retired
+          __syncwarp();
+          if (++xs == (uint32_t)p.x_ring) { xs = 0; xph ^= 1u; }
+        }
+        if (elect_one()) umma_commit(&sync->tfull[acc]);
+        __syncwarp();
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    } else {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       const int ksteps = (int)(p.pitch / 32u);  // UMMA K = 16 elements = 32 bytes
       const uint64_t d_hi = umma_smem_desc(0u, p.pitch);
@@ -266,32 +372,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const int cl = q * 32 + lane;              // cout inside the 128-cout tile
         const int nch = p.ep_nch;
         uint32_t k0 = 0;                           // flat chunk index of the tile's first chunk
+        // residual chunk [32 px][128 couts] = 8 KB: four coalesced 16-byte loads per thread (two 256-byte
+        // pixel rows per warp instruction).  The loads run TWO of this group's chunks ahead of the chunk being
+        // finished (across tile boundaries: `pf` walks the same chunk sequence as the loops below), because under
+        // load an HBM round trip is longer than one chunk; the data is parked in the ring slot and then read back
+        // transposed (thread = cout).
+        const int tig = (warp - 2 - 4 * grp) * 32 + lane;      // thread index inside the group (0..127)
+        struct { int t, qq; uint32_t k0; TileCoord c; } pf;
+        pf.t = blockIdx.x; pf.k0 = 0; pf.qq = grp;
+        if (pf.t < p.total_tiles) pf.c = decode_tile(p, pf.t);
+        auto pf_settle = [&]() {                   // move to the next tile while this group owns no chunk of it
+          while (pf.t < p.total_tiles && pf.qq >= nch) {
+            pf.k0 += (uint32_t)nch;
+            pf.t += gridDim.x;
+            if (pf.t < p.total_tiles) { pf.c = decode_tile(p, pf.t); pf.qq = (int)((pf.k0 ^ (uint32_t)grp) & 1u); }
+          }
+        };
+        auto pf_load = [&](uint4 (&r)[4]) {        // load the chunk `pf` points at (zeros past the end), advance
+          pf_settle();
+          const bool ok = pf.t < p.total_tiles;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = u * 128 + tig, i = idx >> 4, part = idx & 15;
+            const int j = pf.qq * kEpChunkPx + i;
+            const int oy = pf.c.oy0 + (j >> p.tw_shift), ox = pf.c.ox0 + (j & (p.TW - 1));
+            r[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok && oy < p.OH && ox < p.OW && !(p.dbg & 4))
+              r[u] = __ldg(reinterpret_cast<const uint4*>(
+                  res16 + (((size_t)pf.c.n * p.OH + oy) * p.OW + ox) * p.res_pitch + p.res_coff + pf.c.ot * 128 +
+                  part * 8));
+          }
+          pf.qq += 2;
+        };
+        uint4 r0[4], r1[4], r2[4];
+        if (p.has_res) { pf_load(r0); pf_load(r1); }
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
           const TileCoord c = decode_tile(p, t);
           const bool live = c.je > c.jb;
           const int co = c.ot * 128 + cl;
           const float sc = __ldg(p.scale + co), sh = __ldg(p.shift + co);
           const int relu = co < p.relu_n;
-          // residual chunk [32 px][128 couts] = 8 KB: four coalesced 16-byte loads per thread (two 256-byte
-          // pixel rows per warp instruction), issued one chunk ahead; they are parked in the ring slot and
-          // then read back transposed (thread = cout) exactly like the TMA-delivered residual used to be
-          const int tig = (warp - 2 - 4 * grp) * 32 + lane;      // thread index inside the group (0..127)
-          auto load_res = [&](int qq, uint4 (&r)[4]) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int idx = u * 128 + tig, i = idx >> 4, part = idx & 15;
-              const int j = qq * kEpChunkPx + i;
-              const int oy = c.oy0 + (j >> p.tw_shift), ox = c.ox0 + (j & (p.TW - 1));
-              r[u] = make_uint4(0u, 0u, 0u, 0u);
-              if (oy < p.OH && ox < p.OW)
-                r[u] = __ldg(reinterpret_cast<const uint4*>(
-                    res16 + (((size_t)c.n * p.OH + oy) * p.OW + ox) * p.res_pitch + p.res_coff + c.ot * 128 +
-                    part * 8));
-            }
-          };
           int qq = (int)((k0 ^ (uint32_t)grp) & 1u);       // first chunk of this tile owned by this group
-          uint4 rcur[4], rnext[4];
-          if (p.has_res && qq < nch) load_res(qq, rcur);
           if (live) {
             mbar_wait(&sync->tfull[acc], acc_phase);
             tc_fence_after();
@@ -301,12 +422,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             const uint32_t k = k0 + (uint32_t)qq;
             const uint32_t b = k & (kEpRing - 1);
             uint8_t* buf = stg + b * kEpBufBytes;
-            if (p.has_res && qq + 2 < nch) load_res(qq + 2, rnext);
+            if (p.has_res) pf_load(r2);
             mbar_wait(&sync->sfree[b], (k / kEpRing) & 1u);   // the slot's previous store has drained
             if (p.has_res) {
 #pragma unroll
               for (int u = 0; u < 4; ++u)
-                *reinterpret_cast<uint4*>(buf + (u * 128 + tig) * 16) = rcur[u];
+                *reinterpret_cast<uint4*>(buf + (u * 128 + tig) * 16) = r0[u];
               named_bar_sync(1 + grp, 128);           // the whole residual chunk is in the slot
             }
             uint32_t v[32];
@@ -328,7 +449,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             if (lane == 0) mbar_arrive(&sync->sdone[b]);
             if (p.has_res) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) rcur[u] = rnext[u];
+              for (int u = 0; u < 4; ++u) { r0[u] = r1[u]; r1[u] = r2[u]; }
             }
           }
           k0 += (uint32_t)nch;
@@ -480,9 +601,9 @@ static int ilog2(int v) {
   return r;
 }
 
-template <int MODE, int DT>
+template <int MODE, int DT, bool ROW = false>
 static int set_attr(size_t smem) {
-  DRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, DT>,
+  DRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, DT, ROW>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return DRNB200_OK;
 }
@@ -538,8 +659,27 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   stages = std::max(2, std::min(stages, kMaxStages));
   p.stages = stages;
   plan->smem_bytes = kMaxSmem;
+  // ---- ROW variant: 3x3 stride-1 convs over 64-channel K-blocks whose tile is one 256-pixel row segment
+  static const char* env_row = getenv("DRNB200_ROW");       // A/B knob: "0" keeps the per-tap pipeline
+  p.row_mode = 0;
+  static const char* env_dbg = getenv("DRNB200_DBG");        // timing diagnostics of the ROW mainloop (results invalid):
+  p.dbg = env_dbg ? atoi(env_dbg) : 0;                       // 1 no weight loads, 2 no row loads, 4 no residual loads
+  if (mode == MODE_T && p.taps == 9 && d.stride == 1 && p.tile_ci == 64 && d.dilation <= 4 && TW == kRowPx &&
+      TH == 1 && !(env_row && env_row[0] == '0')) {
+    static const char* env_ring = getenv("DRNB200_ROW_RING");   // "x,w" ring sizes for tuning
+    int xr = 3, wr = 5;
+    if (env_ring && sscanf(env_ring, "%d,%d", &xr, &wr) != 2) { xr = 3; wr = 5; }
+    xr = std::max(2, std::min(xr, kMaxXRing));
+    wr = std::max(2, std::min(wr, kMaxStages));
+    while ((size_t)xr * kRowBytes + (size_t)wr * kRowWBytes + fixed > kMaxSmem && wr > 2) --wr;
+    p.row_mode = 1; p.x_ring = xr; p.w_ring = wr;
+    p.main_bytes = (uint32_t)(xr * kRowBytes + wr * kRowWBytes);
+  }
   int rc;
-  if (mode == MODE_T)
+  if (mode == MODE_T && p.row_mode)
+    rc = (d.act_dtype == DRNB200_BF16) ? set_attr<MODE_T, DRNB200_BF16, true>(plan->smem_bytes)
+                                       : set_attr<MODE_T, DRNB200_F16, true>(plan->smem_bytes);
+  else if (mode == MODE_T)
     rc = (d.act_dtype == DRNB200_BF16) ? set_attr<MODE_T, DRNB200_BF16>(plan->smem_bytes)
                                        : set_attr<MODE_T, DRNB200_F16>(plan->smem_bytes);
   else if (mode == MODE_TD)
@@ -624,6 +764,17 @@ static int encode_tmap(drnb200_conv_plan* plan, const void* x) {
               (int)r, p.Cin, p.W, p.H, p.N, box[0], box[1], box[2]);
     return DRNB200_E_CUDA;
   }
+  if (p.row_mode) {                       // the 8 halo pixels right of the 256-pixel row box
+    cuuint32_t box2[4] = {64, (cuuint32_t)(kRowHaloPx - kRowPx), 1, 1};
+    r = fn(&plan->tmap_x2, dt, 4, const_cast<void*>(x), gdim, gstr, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(row halo) failed with CUresult %d", (int)r);
+      return DRNB200_E_CUDA;
+    }
+  } else {
+    plan->tmap_x2 = plan->tmap;
+  }
   plan->tmap_ptr = x;
   return DRNB200_OK;
 }
@@ -656,10 +807,13 @@ int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   const bool bf = plan->d.act_dtype == DRNB200_BF16;
 #define DRN_LAUNCH(M)                                                                                   \
   do {                                                                                                  \
-    if (bf) conv_tc_kernel<M, DRNB200_BF16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, p); \
-    else    conv_tc_kernel<M, DRNB200_F16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, p);  \
+    if (bf) conv_tc_kernel<M, DRNB200_BF16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p); \
+    else    conv_tc_kernel<M, DRNB200_F16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);  \
   } while (0)
-  if (plan->tc_mode == MODE_T) DRN_LAUNCH(MODE_T);
+  if (plan->tc_mode == MODE_T && p.row_mode) {
+    if (bf) conv_tc_kernel<MODE_T, DRNB200_BF16, true><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);
+    else    conv_tc_kernel<MODE_T, DRNB200_F16, true><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);
+  } else if (plan->tc_mode == MODE_T) DRN_LAUNCH(MODE_T);
   else if (plan->tc_mode == MODE_TD) DRN_LAUNCH(MODE_TD);
   else DRN_LAUNCH(MODE_P);
 #undef DRN_LAUNCH
