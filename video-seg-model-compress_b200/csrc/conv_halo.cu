@@ -23,17 +23,26 @@
 
 namespace drnb200 {
 
-constexpr int H_EPI_GROUPS = 2;         // epilogue groups of four warps, one tile each, round-robin
-constexpr int H_MMA_WARPS = 2;          // MMA-issuing warps on alternate tiles: the per-tile wait/commit
+#ifndef DRN_H_EPI_GROUPS
+#define DRN_H_EPI_GROUPS 2
+#endif
+#ifndef DRN_H_MMA_WARPS
+#define DRN_H_MMA_WARPS 2
+#endif
+#ifndef DRN_H_ACC
+#define DRN_H_ACC 4
+#endif
+constexpr int H_EPI_GROUPS = DRN_H_EPI_GROUPS;         // epilogue groups of four warps, one tile each, round-robin
+constexpr int H_MMA_WARPS = DRN_H_MMA_WARPS;          // MMA-issuing warps on alternate tiles: the per-tile wait/commit
                                         // latency of one issuer (~800 cycles) bounded the small layers
 constexpr int H_W_EPI = 1 + H_MMA_WARPS;
 constexpr int H_THREADS = (H_W_EPI + 4 * H_EPI_GROUPS) * 32;
 constexpr int H_TW = 8, H_TH = 16;      // output tile (pixels)
 constexpr int H_WP = 16;                // halo row length in pixels (8 + 2*dil <= 16)
 constexpr int H_MAX_RING = 6;
-constexpr int H_ACC = 4;                // TMEM accumulator stages: the MMA -> epilogue -> MMA round trip is
+constexpr int H_ACC = DRN_H_ACC;                // TMEM accumulator stages: the MMA -> epilogue -> MMA round trip is
                                         // ~3000 cycles, far longer than a tile of these small layers
-constexpr uint32_t H_TMEM_COLS = 256;   // 4 accumulators x 64 columns
+constexpr uint32_t H_TMEM_COLS = H_ACC * 64;   // accumulators x 64 columns
 
 struct HaloParams {
   const void* x;
@@ -47,7 +56,8 @@ struct HaloParams {
   int tiles_x, tiles_y, total_tiles, halo_h, ring;
   uint32_t magic_x, magic_y;   // ceil(2^32 / tiles_{x,y}): exact quotients by __umulhi for t < 2^32 / divisor
   uint32_t pitch, halo_bytes, w_tile_bytes, idesc, base_off_mode;
-  int dbg;                   // diagnostics (DRNB200_DBG): 1 = issue one tap only, 2 = skip the global stores
+  int dbg;                   // diagnostics (DRNB200_DBG): 1 = issue one tap only, 2 = skip the global stores,
+                             // 4 = load two halo rows only (is the halo TMA the bound?)
 };
 
 struct __align__(16) HSync {
@@ -129,7 +139,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
         const HTile c = h_decode(p, t);
         mbar_wait(&sync->h_empty[b], bph ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&sync->h_full[b], p.halo_bytes);
+          mbar_arrive_expect_tx(&sync->h_full[b], p.dbg == 4 ? 2u * H_WP * p.pitch : p.halo_bytes);
           // tensor {Cin, W, H, N}; box {Cin, 16, 16+2d, 1}; zero fill outside the image = conv padding
           tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_bytes, 0, c.ox0 - p.dil,
                       c.oy0 - p.dil, c.n);
@@ -333,7 +343,7 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
     cuuint64_t gdim[4] = {(cuuint64_t)c.Cin, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
     cuuint64_t gstr[3] = {(cuuint64_t)c.x_cpitch * 2, (cuuint64_t)c.W * c.x_cpitch * 2,
                           (cuuint64_t)c.H * c.W * c.x_cpitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)c.Cin, (cuuint32_t)H_WP, (cuuint32_t)p.halo_h, 1};
+    cuuint32_t box[4] = {(cuuint32_t)c.Cin, (cuuint32_t)H_WP, (cuuint32_t)(p.dbg == 4 ? 2 : p.halo_h), 1};   // dbg 4: timing probe
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMapSwizzle sw = p.pitch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                             : p.pitch == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;

@@ -347,7 +347,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             // (k-4 <= k-1-D) and is complete once at most one newer store is still reading
             if (elect_one()) {
               bulk_wait_group_read<1>();
-              mbar_arrive(&sync->sfree[b]);
+              if (p.res_tma) {                      // residual chunk [32 px][128 couts] straight into the slot
+                mbar_arrive_expect_tx(&sync->rfull[b], kEpBufBytes);
+                tma_load_4d(&tmap_r, &sync->rfull[b], stg + b * kEpBufBytes, p.res_coff + c.ot * 128, cx, cy, c.n);
+              } else {
+                mbar_arrive(&sync->sfree[b]);
+              }
             }
             __syncwarp();
             hist_ot[k % D] = c.ot; hist_cx[k % D] = cx; hist_cy[k % D] = cy; hist_n[k % D] = c.n;
@@ -405,7 +410,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           pf.qq += 2;
         };
         uint4 r0[4], r1[4], r2[4];
-        if (p.has_res) { pf_load(r0); pf_load(r1); }
+        const bool res_regs = p.has_res && !p.res_tma;     // residual through registers (A/B knob DRNB200_RES=regs)
+        if (res_regs) { pf_load(r0); pf_load(r1); }
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
           const TileCoord c = decode_tile(p, t);
           const bool live = c.je > c.jb;
@@ -422,13 +428,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             const uint32_t k = k0 + (uint32_t)qq;
             const uint32_t b = k & (kEpRing - 1);
             uint8_t* buf = stg + b * kEpBufBytes;
-            if (p.has_res) pf_load(r2);
-            mbar_wait(&sync->sfree[b], (k / kEpRing) & 1u);   // the slot's previous store has drained
-            if (p.has_res) {
+            if (res_regs) pf_load(r2);
+            if (p.res_tma) {
+              mbar_wait(&sync->rfull[b], (k / kEpRing) & 1u);   // slot drained AND the residual chunk has landed
+            } else {
+              mbar_wait(&sync->sfree[b], (k / kEpRing) & 1u);   // the slot's previous store has drained
+              if (res_regs) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                *reinterpret_cast<uint4*>(buf + (u * 128 + tig) * 16) = r0[u];
-              named_bar_sync(1 + grp, 128);           // the whole residual chunk is in the slot
+                for (int u = 0; u < 4; ++u)
+                  *reinterpret_cast<uint4*>(buf + (u * 128 + tig) * 16) = r0[u];
+                named_bar_sync(1 + grp, 128);         // the whole residual chunk is in the slot
+              }
             }
             uint32_t v[32];
             if (live) {
@@ -447,7 +457,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             fence_proxy_async_smem();              // st.shared -> visible to the TMA store
             __syncwarp();
             if (lane == 0) mbar_arrive(&sync->sdone[b]);
-            if (p.has_res) {
+            if (res_regs) {
 #pragma unroll
               for (int u = 0; u < 4; ++u) { r0[u] = r1[u]; r1[u] = r2[u]; }
             }
@@ -661,6 +671,8 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   plan->smem_bytes = kMaxSmem;
   // ---- ROW variant: 3x3 stride-1 convs over 64-channel K-blocks whose tile is one 256-pixel row segment
   static const char* env_row = getenv("DRNB200_ROW");       // A/B knob: "0" keeps the per-tap pipeline
+  static const char* env_res = getenv("DRNB200_RES");        // A/B knob: "regs" = residual through registers
+  p.res_tma = (mode == MODE_T && p.has_res && !(env_res && env_res[0] == 'r')) ? 1 : 0;
   p.row_mode = 0;
   static const char* env_dbg = getenv("DRNB200_DBG");        // timing diagnostics of the ROW mainloop (results invalid):
   p.dbg = env_dbg ? atoi(env_dbg) : 0;                       // 1 no weight loads, 2 no row loads, 4 no residual loads
@@ -711,17 +723,18 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   return DRNB200_OK;
 }
 
-// output-shaped NHWC tensor, box = one staged chunk (128 couts x ep_cw x ep_ch pixels), no swizzle
-static int encode_out_tmap(drnb200_conv_plan* plan, CUtensorMap* map, const void* ptr) {
+// output-shaped NHWC tensor, box = one staged chunk (128 couts x ep_cw x ep_ch pixels), no swizzle;
+// `cpitch` = channels per pixel of the tensor the pointer lives in (the residual may be a channel sub-range)
+static int encode_out_tmap(drnb200_conv_plan* plan, CUtensorMap* map, const void* ptr, int cpitch) {
   const ConvParams& p = plan->p;
   auto fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return DRNB200_E_CUDA;
   }
-  cuuint64_t gdim[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.N};
-  cuuint64_t gstr[3] = {(cuuint64_t)p.Cout * 2, (cuuint64_t)p.OW * p.Cout * 2,
-                        (cuuint64_t)p.OH * p.OW * p.Cout * 2};
+  cuuint64_t gdim[4] = {(cuuint64_t)cpitch, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.N};
+  cuuint64_t gstr[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)p.OW * cpitch * 2,
+                        (cuuint64_t)p.OH * p.OW * cpitch * 2};
   cuuint32_t box[4] = {128, (cuuint32_t)p.ep_cw, (cuuint32_t)p.ep_ch, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMapDataType dt = plan->d.act_dtype == DRNB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
@@ -787,12 +800,12 @@ int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   }
   if (plan->tc_mode == MODE_T) {
     if (plan->tmap_y_ptr != p.y) {
-      int rc = encode_out_tmap(plan, &plan->tmap_y, p.y);
+      int rc = encode_out_tmap(plan, &plan->tmap_y, p.y, p.Cout);
       if (rc) return rc;
       plan->tmap_y_ptr = p.y;
     }
     if (p.has_res && plan->tmap_r_ptr != p.residual) {
-      int rc = encode_out_tmap(plan, &plan->tmap_r, p.residual);
+      int rc = encode_out_tmap(plan, &plan->tmap_r, p.residual, p.res_pitch);
       if (rc) return rc;
       plan->tmap_r_ptr = p.residual;
     }
