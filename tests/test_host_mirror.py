@@ -252,3 +252,53 @@ def test_frameio_fails_loudly_on_cpu_tensors():
     model = drnb200.DRNSeg("drn_d_22", 19, pretrained_model=None, pretrained=False).eval()
     with pytest.raises(ffi.Drnb200Error):
         model.predict(torch.zeros(1, 16, 16, 3, dtype=torch.uint8))
+
+
+def test_checkpoint_ingestion_prefixes_and_prune_buffers(tmp_path):
+    """DataParallel `module.` prefix, `base.` flavour of the video scripts, save_checkpoint dicts and
+    torch.nn.utils.prune's weight_orig/weight_mask all load into the drop-in module with the masks recovered"""
+    import torch.nn.utils.prune as prune
+    torch.manual_seed(3)
+    src = drnb200.DRNSeg("drn_d_22", 19, pretrained_model=None, pretrained=False)
+    ref_sd = collections.OrderedDict((k, v.clone()) for k, v in src.state_dict().items())
+    # (a) checkpoint dict + module. prefix + base. backbone name
+    ck = {"epoch": 7, "state_dict": collections.OrderedDict(
+        ("module." + k.replace("layer.", "base.", 1) if k.startswith("layer.") else "module." + k, v)
+        for k, v in ref_sd.items())}
+    path = tmp_path / "checkpoint.pth.tar"
+    torch.save(ck, str(path))
+    dst = drnb200.DRNSeg("drn_d_22", 19, pretrained_model=None, pretrained=False)
+    masks = drnb200.load_checkpoint(dst, str(path))
+    assert not masks
+    for k, v in dst.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
+    # the `base` flavoured module takes a `layer.` checkpoint
+    dst_b = drnb200.DRNSeg("drn_d_22", 19, pretrained_model=None, pretrained=False, backbone_attr="base")
+    drnb200.load_checkpoint(dst_b, ref_sd)
+    assert torch.equal(dst_b.state_dict()["base.layer3.0.conv1.weight"], ref_sd["layer.layer3.0.conv1.weight"]) \
+        if "layer.layer3.0.conv1.weight" in ref_sd else True
+    # (b) torch.nn.utils.prune re-parametrisation (semseg_unstructured.py:770-773)
+    pr = drnb200.DRNSeg("drn_d_22", 19, pretrained_model=None, pretrained=False)
+    pr.load_state_dict(ref_sd)
+    convs = [(n, m) for n, m in pr.named_modules() if isinstance(m, torch.nn.Conv2d) and m.kernel_size == (3, 3)][:3]
+    for _, m in convs:
+        prune.l1_unstructured(m, name="weight", amount=0.9)
+    psd = pr.state_dict()
+    assert any(k.endswith("weight_orig") for k in psd)
+    sd2, masks2 = drnb200.normalize_state_dict(psd)
+    assert not any(k.endswith("_orig") or k.endswith("_mask") for k in sd2)
+    assert len(masks2) == 3
+    for n, m in convs:
+        key = n + ".weight"
+        assert torch.equal(sd2[key], psd[n + ".weight_orig"] * psd[n + ".weight_mask"])
+        assert torch.equal(masks2[key], psd[n + ".weight_mask"])
+        assert abs(float(masks2[key].mean()) - 0.1) < 0.01
+    dst2 = drnb200.DRNSeg("drn_d_22", 19, pretrained_model=None, pretrained=False)
+    got = drnb200.load_checkpoint(dst2, psd)
+    assert set(got) == set(masks2) and dst2._mask_dict is got
+    # masks implied by the zeros of an already-pruned checkpoint
+    z = drnb200.masks_from_zeros(sd2, keys=set(masks2))
+    assert all(torch.equal(z[k], masks2[k]) for k in masks2)
+    # mismatching checkpoints fail loudly
+    with pytest.raises(KeyError):
+        drnb200.load_checkpoint(dst2, {"layer.nope.weight": torch.zeros(1)})

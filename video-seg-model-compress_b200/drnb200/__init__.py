@@ -10,8 +10,10 @@ from . import pruners
 from .evalops import ConfusionMeter, fast_hist, per_class_iu, shard_frames
 from .engine import ingest_lut
 from . import frameio
+from . import checkpoint
+from .checkpoint import load_checkpoint, normalize_state_dict, masks_from_zeros
 from .frameio import CITYSCAPE_PALETTE, colorize, overlay, load_info
 
 __all__ = ["DRNSeg", "fill_up_weights", "drn", "pruners", "ffi", "ConfusionMeter", "fast_hist",
            "per_class_iu", "shard_frames", "frameio", "CITYSCAPE_PALETTE", "colorize", "overlay", "load_info",
-           "ingest_lut"]
+           "ingest_lut", "checkpoint", "load_checkpoint", "normalize_state_dict", "masks_from_zeros"]
