@@ -44,6 +44,20 @@ template <> struct Act<DRNB200_F16> {
   }
 };
 
+
+// two floats -> one 32-bit word of two act_dtype values (round to nearest even), lo in the low half
+template <int DT> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<DRNB200_F16>(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <> __device__ __forceinline__ uint32_t pack2<DRNB200_BF16>(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // Byte offset of 16-byte chunk `chunk` of row `row` inside a K-major tile whose rows are
 // `pitch` bytes (32, 64 or 128) and whose 16-byte chunks are XOR-swizzled the way TMA / UMMA
 // SWIZZLE_{32,64,128}B do (address bits [4,4+B) ^= bits [7,7+B), B = log2(pitch/16)).

@@ -4,10 +4,10 @@
 // Why: for the narrow layers (DRN layer1: 16->16 at full resolution, layer3: 64->64 at 1/4) the per-tap
 // TMA path of conv_tc.cu moves every input pixel L2->SM nine times and is bound by that traffic
 // (layer3: 0.23 ms per conv at batch 8 vs a 0.04 ms HBM floor).  Here one TMA box per tile brings the halo
-//   [16+2d rows][16 pixels][Cin channels]      (pixel rows of `pitch` = Cin*2 bytes, SWIZZLE_{32,64,128}B)
-// and tap (ky,kx) of the 8x16-pixel output tile is the UMMA A operand whose descriptor simply starts
-// (ky*d*16 + kx*d) pixel rows further: M row m = (ty, tx) -> 8-row group ty (stride = one halo row =
-// 16*pitch bytes, a multiple of the swizzle atom) and row tx inside it.  Measured on B200: the UMMA swizzle
+//   [16+2d rows][24 pixels][Cin channels]      (pixel rows of `pitch` = Cin*2 bytes, SWIZZLE_{32,64,128}B)
+// and tap (ky,kx) of M-block mb (8x16 pixels) of the 16x16-pixel output tile is the UMMA A operand whose descriptor
+// simply starts (ky*d*24 + kx*d + 8*mb) pixel rows further: M row m = (ty, tx) -> 8-row group ty (stride = one halo
+// row = 24*pitch bytes, a multiple of the swizzle atom) and row tx inside it.  Measured on B200: the UMMA swizzle
 // XOR is taken from the ABSOLUTE shared-memory address bits (like TMA's), so a start that is not atom
 // aligned needs no compensation — the descriptor base-offset field must stay 0 (setting it to
 // (start >> 7) & 7 gives wrong results; DRNB200_HALO=1 reproduces that for the record).
@@ -27,18 +27,21 @@ namespace drnb200 {
 #define DRN_H_EPI_GROUPS 2
 #endif
 #ifndef DRN_H_MMA_WARPS
-#define DRN_H_MMA_WARPS 2
+#define DRN_H_MMA_WARPS 3
 #endif
 #ifndef DRN_H_ACC
-#define DRN_H_ACC 4
+#define DRN_H_ACC 8
 #endif
 constexpr int H_EPI_GROUPS = DRN_H_EPI_GROUPS;         // epilogue groups of four warps, one tile each, round-robin
 constexpr int H_MMA_WARPS = DRN_H_MMA_WARPS;          // MMA-issuing warps on alternate tiles: the per-tile wait/commit
                                         // latency of one issuer (~800 cycles) bounded the small layers
 constexpr int H_W_EPI = 1 + H_MMA_WARPS;
 constexpr int H_THREADS = (H_W_EPI + 4 * H_EPI_GROUPS) * 32;
-constexpr int H_TW = 8, H_TH = 16;      // output tile (pixels)
-constexpr int H_WP = 16;                // halo row length in pixels (8 + 2*dil <= 16)
+constexpr int H_MB = 2;                 // UMMA M-blocks (8 x 16 pixels each) per tile, side by side in x: the per-tile
+                                        // barrier/commit skeleton alone costs ~320 cycles (measured with every load, MMA
+                                        // and epilogue body switched off), so a tile carries 256 pixels, not 128
+constexpr int H_TW = 8 * H_MB, H_TH = 16;   // output tile (pixels)
+constexpr int H_WP = H_TW + 8;          // halo row length in pixels (H_TW + 2*dil, dil <= 4), a multiple of 8
 constexpr int H_MAX_RING = 6;
 constexpr int H_ACC = DRN_H_ACC;                // TMEM accumulator stages: the MMA -> epilogue -> MMA round trip is
                                         // ~3000 cycles, far longer than a tile of these small layers
@@ -54,10 +57,12 @@ struct HaloParams {
   const float* shift;
   int n_kb, N, H, W, Cin, Cout, dil, relu_n, has_res, x_cpitch, res_pitch, res_coff;
   int tiles_x, tiles_y, total_tiles, halo_h, ring;
+  int n_mma;                 // MMA-issuing warps in use: min(H_MMA_WARPS, ring) (each owns every n_mma-th ring slot)
   uint32_t magic_x, magic_y;   // ceil(2^32 / tiles_{x,y}): exact quotients by __umulhi for t < 2^32 / divisor
-  uint32_t pitch, halo_bytes, w_tile_bytes, idesc, base_off_mode;
+  uint32_t pitch, halo_bytes, halo_tx, w_tile_bytes, idesc, base_off_mode;   // halo_bytes: ring slot stride, halo_tx: box bytes
   int dbg;                   // diagnostics (DRNB200_DBG): 1 = issue one tap only, 2 = skip the global stores,
-                             // 4 = load two halo rows only (is the halo TMA the bound?)
+                             // 4 = load two halo rows only (is the halo TMA the bound?); bits 8 / 16 / 32 = skip the
+                             // epilogue body / all MMAs / the halo loads (pipeline skeleton)
 };
 
 struct __align__(16) HSync {
@@ -92,7 +97,7 @@ __device__ __forceinline__ uint64_t umma_desc_ex(uint32_t addr, uint32_t pitch, 
   return d;
 }
 
-template <int DT, int KSTEPS>
+template <int DT, int KSTEPS, bool HAS_RES>
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -138,8 +143,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const HTile c = h_decode(p, t);
         mbar_wait(&sync->h_empty[b], bph ^ 1u);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&sync->h_full[b], p.dbg == 4 ? 2u * H_WP * p.pitch : p.halo_bytes);
+        if (p.dbg & 32) {
+          if (elect_one()) mbar_arrive(&sync->h_full[b]);
+        } else if (elect_one()) {
+          mbar_arrive_expect_tx(&sync->h_full[b], p.dbg == 4 ? 2u * H_WP * p.pitch : p.halo_tx);
           // tensor {Cin, W, H, N}; box {Cin, 16, 16+2d, 1}; zero fill outside the image = conv padding
           tma_load_4d(&tmap_x, &sync->h_full[b], halo + (size_t)b * p.halo_bytes, 0, c.ox0 - p.dil,
                       c.oy0 - p.dil, c.n);
@@ -167,33 +174,38 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
         const int ky = tap / 3, kx = tap - ky * 3;
         a_off16[kb] = ((uint32_t)(ky * p.dil) * row_bytes + (uint32_t)(kx * p.dil) * p.pitch) >> 4;
       }
-      const int n_kb = p.dbg == 1 ? 1 : p.n_kb;
+      const int n_kb = p.dbg == 1 ? 1 : ((p.dbg & 16) ? 0 : p.n_kb);
+      const uint32_t mb16 = (8u * p.pitch) >> 4;             // M-block mb starts 8 pixels further right
       const int mw = warp - 1;                               // this warp takes tiles i = mw, mw + H_MMA_WARPS, ...
-      int i = mw, b = mw % p.ring;
-      uint32_t bph = (uint32_t)(mw / p.ring) & 1u;
-      for (int t = blockIdx.x + mw * gridDim.x; t < p.total_tiles; t += H_MMA_WARPS * gridDim.x, i += H_MMA_WARPS) {
-        const int acc = i % H_ACC;
+      int i = mw, b = mw;                                    // mw < n_mma <= ring
+      uint32_t bph = 0;
+      for (int t = blockIdx.x + mw * gridDim.x; mw < p.n_mma && t < p.total_tiles;
+           t += p.n_mma * gridDim.x, i += p.n_mma) {
+        const int acc = (i * H_MB) % H_ACC;                  // tile i owns accumulators acc .. acc + H_MB - 1
         mbar_wait(&sync->h_full[b], bph);
-        mbar_wait(&sync->t_empty[acc], ((uint32_t)(i / H_ACC) & 1u) ^ 1u);
+        mbar_wait(&sync->t_empty[acc], ((uint32_t)(i * H_MB / H_ACC) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t h16 = smem_u32(halo + (size_t)b * p.halo_bytes) >> 4;
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 64u;
         if (elect_one()) {
 #pragma unroll
-          for (int kb = 0; kb < 9; ++kb) {
-            if (kb < n_kb) {
+          for (int mb = 0; mb < H_MB; ++mb) {
 #pragma unroll
-              for (int ks = 0; ks < KSTEPS; ++ks)
-                umma_f16(d_tmem, a_hi | (uint64_t)(h16 + a_off16[kb] + 2u * ks),
-                         b_hi | (uint64_t)(w16 + (uint32_t)kb * wt16 + 2u * ks), p.idesc,
-                         (kb > 0 || ks > 0) ? 1u : 0u);
+            for (int kb = 0; kb < 9; ++kb) {
+              if (kb < n_kb) {
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks)
+                  umma_f16(d_tmem + (uint32_t)mb * 64u, a_hi | (uint64_t)(h16 + a_off16[kb] + mb * mb16 + 2u * ks),
+                           b_hi | (uint64_t)(w16 + (uint32_t)kb * wt16 + 2u * ks), p.idesc,
+                           (kb > 0 || ks > 0) ? 1u : 0u);
+              }
             }
           }
           umma_commit(&sync->h_empty[b]);
           umma_commit(&sync->t_full[acc]);
         }
         __syncwarp();
-        b += H_MMA_WARPS;
+        b += p.n_mma;
         if (b >= p.ring) { b -= p.ring; bph ^= 1u; }
       }
     }
@@ -204,58 +216,90 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
     const int m = q * 32 + lane;                    // TMEM lane = pixel (ty = m / 8, tx = m % 8)
     const uint16_t* res16 = reinterpret_cast<const uint16_t*>(p.residual);
     uint16_t* y16 = reinterpret_cast<uint16_t*>(p.y);
+    // One tile = H_MB M-blocks = H_MB pixels per thread; the M-blocks' instruction streams run interleaved (one warp
+    // finishing one M-block is a ~200-instruction dependent chain).
+    static_assert(H_MB == 2 && H_ACC % H_MB == 0, "the epilogue below is written for two M-blocks per tile");
+    const bool relu_all = p.relu_n >= p.Cout;       // the usual case: one warp-uniform branch instead of 16 predicates
+    constexpr bool has1 = true;
     for (int i = grp, t = blockIdx.x + grp * gridDim.x; t < p.total_tiles;
          t += H_EPI_GROUPS * gridDim.x, i += H_EPI_GROUPS) {
-      const int acc = i % H_ACC;
+      const int acc = (i * H_MB) % H_ACC;
+      const uint32_t tph = (uint32_t)(i * H_MB / H_ACC) & 1u;
       const HTile c = h_decode(p, t);
-      const int ox = c.ox0 + (m & (H_TW - 1)), oy = c.oy0 + (m >> 3);
-      const bool valid = ox < p.W && oy < p.H;
-      const size_t pix0 = ((size_t)c.n * p.H + oy) * p.W + ox;
-      const size_t off0 = pix0 * p.Cout;
+      bool valid[2];
+      size_t pix0[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int ox = c.ox0 + 8 * u + (m & 7), oy = c.oy0 + (m >> 3);
+        valid[u] = ox < p.W && oy < p.H;
+        pix0[u] = ((size_t)c.n * p.H + oy) * p.W + ox;
+      }
       // the residual of this pixel (<= 128 B) is requested before the accumulator wait so that its
       // latency overlaps the MMAs instead of serialising behind every 16-channel group
-      uint4 rv[8];
+      uint4 rv[2][8];
+      if (HAS_RES) {
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        rv[g] = make_uint4(0u, 0u, 0u, 0u);
-        if (p.has_res && valid && g * 8 < p.Cout)
-          rv[g] = __ldg(reinterpret_cast<const uint4*>(res16 + pix0 * p.res_pitch + p.res_coff) + g);
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            rv[u][g] = make_uint4(0u, 0u, 0u, 0u);
+            if (valid[u] && g * 8 < p.Cout)
+              rv[u][g] = __ldg(reinterpret_cast<const uint4*>(res16 + pix0[u] * p.res_pitch + p.res_coff) + g);
+          }
       }
-      mbar_wait(&sync->t_full[acc], (uint32_t)(i / H_ACC) & 1u);
+      mbar_wait(&sync->t_full[acc], tph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)acc * 64u + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int cbi = 0; cbi < 4; ++cbi) {
         const int cb = cbi * 16;
-        if (cb < p.Cout) {
-          uint32_t v[16];
-          tmem_ld16(t_addr + (uint32_t)cb, v);
+        if (cb < p.Cout && !(p.dbg & 8)) {
+          uint32_t v[2][16];
+          tmem_ld16(t_addr + (uint32_t)cb, v[0]);
+          if (has1) tmem_ld16(t_addr + 64u + (uint32_t)cb, v[1]);
           tmem_ld_wait();
-          if (valid) {
-            const uint32_t rw[8] = {rv[2 * cbi].x, rv[2 * cbi].y, rv[2 * cbi].z, rv[2 * cbi].w,
-                                    rv[2 * cbi + 1].x, rv[2 * cbi + 1].y, rv[2 * cbi + 1].z, rv[2 * cbi + 1].w};
-            uint32_t w[8];
+          float4 sc[4], sh[4];
 #pragma unroll
-            for (int e4 = 0; e4 < 4; ++e4) {
-              const float4 sc = *reinterpret_cast<const float4*>(&sync->scale[cb + 4 * e4]);
-              const float4 sh = *reinterpret_cast<const float4*>(&sync->shift[cb + 4 * e4]);
-              const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+          for (int e4 = 0; e4 < 4; ++e4) {
+            sc[e4] = *reinterpret_cast<const float4*>(&sync->scale[cb + 4 * e4]);
+            sh[e4] = *reinterpret_cast<const float4*>(&sync->shift[cb + 4 * e4]);
+          }
 #pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                const int e = 2 * e4 + h2;     // output word e holds channels cb+2e, cb+2e+1
-                float a = fmaf(__uint_as_float(v[2 * e]), scv[2 * h2], shv[2 * h2]) +
-                          Act<DT>::to_f32((uint16_t)(rw[e] & 0xFFFFu));
-                float d = fmaf(__uint_as_float(v[2 * e + 1]), scv[2 * h2 + 1], shv[2 * h2 + 1]) +
-                          Act<DT>::to_f32((uint16_t)(rw[e] >> 16));
-                if (cb + 2 * e < p.relu_n) a = fmaxf(a, 0.f);
-                if (cb + 2 * e + 1 < p.relu_n) d = fmaxf(d, 0.f);
-                w[e] = (uint32_t)Act<DT>::from_f32(a) | ((uint32_t)Act<DT>::from_f32(d) << 16);
+          for (int u = 0; u < 2; ++u) {
+            if (valid[u]) {
+              float f[16];
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                f[4 * e4] = fmaf(__uint_as_float(v[u][4 * e4]), sc[e4].x, sh[e4].x);
+                f[4 * e4 + 1] = fmaf(__uint_as_float(v[u][4 * e4 + 1]), sc[e4].y, sh[e4].y);
+                f[4 * e4 + 2] = fmaf(__uint_as_float(v[u][4 * e4 + 2]), sc[e4].z, sh[e4].z);
+                f[4 * e4 + 3] = fmaf(__uint_as_float(v[u][4 * e4 + 3]), sc[e4].w, sh[e4].w);
               }
-            }
-            uint4* o = reinterpret_cast<uint4*>(y16 + off0 + cb);
-            if (p.dbg != 2 || w[0] == 0x12345678u) {
-              o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-              o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+              if (HAS_RES) {
+                const uint4 ra = rv[u][2 * cbi], rb = rv[u][2 * cbi + 1];
+                const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[2 * e] += Act<DT>::to_f32((uint16_t)(rw[e] & 0xFFFFu));
+                  f[2 * e + 1] += Act<DT>::to_f32((uint16_t)(rw[e] >> 16));
+                }
+              }
+              if (relu_all) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if (cb + e < p.relu_n) f[e] = fmaxf(f[e], 0.f);
+              }
+              uint32_t w[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w[e] = pack2<DT>(f[2 * e], f[2 * e + 1]);
+              uint4* o = reinterpret_cast<uint4*>(y16 + pix0[u] * p.Cout + cb);
+              if (p.dbg != 2 || w[0] == 0x12345678u) {
+                o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+              }
             }
           }
         }
@@ -312,8 +356,8 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   p.has_res = c.has_res; p.x_cpitch = c.x_cpitch; p.res_pitch = c.res_pitch; p.res_coff = c.res_coff;
   p.pitch = (uint32_t)c.Cin * 2u;
   p.halo_h = H_TH + 2 * c.dil;
-  p.halo_bytes = (uint32_t)p.halo_h * H_WP * p.pitch;
-  p.halo_bytes = (p.halo_bytes + 1023u) & ~1023u;
+  p.halo_tx = (uint32_t)p.halo_h * H_WP * p.pitch;
+  p.halo_bytes = (p.halo_tx + 1023u) & ~1023u;
   p.w_tile_bytes = (uint32_t)c.Cout * p.pitch;
   p.tiles_x = (c.W + H_TW - 1) / H_TW;
   p.tiles_y = (c.H + H_TH - 1) / H_TH;
@@ -333,6 +377,7 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   const size_t fixed = 1024 + ((9u * p.w_tile_bytes + 1023u) & ~1023u) + sizeof(HSync);
   p.ring = (int)std::min<size_t>(H_MAX_RING, (kMaxSmem - fixed) / p.halo_bytes);
   if (p.ring < 2) { set_error("conv_halo: halo tile does not fit shared memory"); return DRNB200_E_ARG; }
+  p.n_mma = std::min(H_MMA_WARPS, p.ring);
 
   static_assert(sizeof(HMapCache) <= sizeof(plan->gather_cache), "halo cache storage too small");
   HMapCache* cache = reinterpret_cast<HMapCache*>(plan->gather_cache);
@@ -364,15 +409,20 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   const int grid = std::min(p.total_tiles, sms);
   if (grid == 0) return DRNB200_OK;
   const int ks = (int)(p.pitch / 32u);
-#define DRN_HALO_LAUNCH(DT, KS)                                                                           \
-  do {                                                                                                    \
-    static bool attr = false;                                                                             \
-    if (!attr) {                                                                                          \
-      DRN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<DT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    (int)kMaxSmem));                                                      \
-      attr = true;                                                                                        \
-    }                                                                                                     \
-    conv_halo_kernel<DT, KS><<<grid, H_THREADS, kMaxSmem, st>>>(cache->map, p);                           \
+#define DRN_HALO_LAUNCH1(DT, KS, RES)                                                                          \
+  do {                                                                                                         \
+    static bool attr = false;                                                                                  \
+    if (!attr) {                                                                                               \
+      DRN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<DT, KS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)kMaxSmem));                                                           \
+      attr = true;                                                                                             \
+    }                                                                                                          \
+    conv_halo_kernel<DT, KS, RES><<<grid, H_THREADS, kMaxSmem, st>>>(cache->map, p);                           \
+  } while (0)
+#define DRN_HALO_LAUNCH(DT, KS)                        \
+  do {                                                 \
+    if (p.has_res) DRN_HALO_LAUNCH1(DT, KS, true);     \
+    else DRN_HALO_LAUNCH1(DT, KS, false);              \
   } while (0)
   if (d.act_dtype == DRNB200_BF16) {
     if (ks == 4) DRN_HALO_LAUNCH(DRNB200_BF16, 4);

@@ -96,18 +96,6 @@ __device__ __forceinline__ TxTile tx_decode(const StemTxParams& p, int t) {
   return c;
 }
 
-template <int DT> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
-template <> __device__ __forceinline__ uint32_t pack2<DRNB200_F16>(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-template <> __device__ __forceinline__ uint32_t pack2<DRNB200_BF16>(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
 // 8 pixels of tensor channel CH out of 24 interleaved bytes (6 words), through the normalisation table
 template <int CH>
 __device__ __forceinline__ uint4 tx_u8_lookup(const uint32_t (&wd)[6], const uint16_t* lut, int xb, int W,
