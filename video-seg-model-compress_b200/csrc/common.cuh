@@ -58,6 +58,18 @@ template <> __device__ __forceinline__ uint32_t pack2<DRNB200_BF16>(float lo, fl
   return r;
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane, 32-byte aligned addresses
+__device__ __forceinline__ void ldg256_nc(const void* p, uint32_t (&a)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&a)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]),
+               "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7])
+               : "memory");
+}
+
 // Byte offset of 16-byte chunk `chunk` of row `row` inside a K-major tile whose rows are
 // `pitch` bytes (32, 64 or 128) and whose 16-byte chunks are XOR-swizzled the way TMA / UMMA
 // SWIZZLE_{32,64,128}B do (address bits [4,4+B) ^= bits [7,7+B), B = log2(pitch/16)).

@@ -224,12 +224,10 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
             float a0 = fmaf(__uint_as_float(v[4 * e4]), sc.x, sh.x), a1 = fmaf(__uint_as_float(v[4 * e4 + 1]), sc.y, sh.y);
             float a2 = fmaf(__uint_as_float(v[4 * e4 + 2]), sc.z, sh.z), a3 = fmaf(__uint_as_float(v[4 * e4 + 3]), sc.w, sh.w);
             if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
-            w[2 * e4] = (uint32_t)Act<DT>::from_f32(a0) | ((uint32_t)Act<DT>::from_f32(a1) << 16);
-            w[2 * e4 + 1] = (uint32_t)Act<DT>::from_f32(a2) | ((uint32_t)Act<DT>::from_f32(a3) << 16);
+            w[2 * e4] = pack2<DT>(a0, a1);
+            w[2 * e4 + 1] = pack2<DT>(a2, a3);
           }
-          uint4* o = reinterpret_cast<uint4*>(yp + cb);
-          o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-          o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          stg256(yp + cb, w);                    // 16 channels = one full 32-byte sector per lane
         }
       }
       tc_fence_before();

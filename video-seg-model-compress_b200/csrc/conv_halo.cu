@@ -236,15 +236,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
       }
       // the residual of this pixel (<= 128 B) is requested before the accumulator wait so that its
       // latency overlaps the MMAs instead of serialising behind every 16-channel group
-      uint4 rv[2][8];
+      uint32_t rv[2][4][8];                           // 32-byte (16-channel) pieces: one full sector per access
       if (HAS_RES) {
 #pragma unroll
         for (int u = 0; u < 2; ++u)
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            rv[u][g] = make_uint4(0u, 0u, 0u, 0u);
-            if (valid[u] && g * 8 < p.Cout)
-              rv[u][g] = __ldg(reinterpret_cast<const uint4*>(res16 + pix0[u] * p.res_pitch + p.res_coff) + g);
+          for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) rv[u][g][e] = 0u;
+            if (valid[u] && g * 16 < p.Cout)
+              ldg256_nc(res16 + pix0[u] * p.res_pitch + p.res_coff + g * 16, rv[u][g]);
           }
       }
       mbar_wait(&sync->t_full[acc], tph);
@@ -276,12 +277,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
                 f[4 * e4 + 3] = fmaf(__uint_as_float(v[u][4 * e4 + 3]), sc[e4].w, sh[e4].w);
               }
               if (HAS_RES) {
-                const uint4 ra = rv[u][2 * cbi], rb = rv[u][2 * cbi + 1];
-                const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  f[2 * e] += Act<DT>::to_f32((uint16_t)(rw[e] & 0xFFFFu));
-                  f[2 * e + 1] += Act<DT>::to_f32((uint16_t)(rw[e] >> 16));
+                  f[2 * e] += Act<DT>::to_f32((uint16_t)(rv[u][cbi][e] & 0xFFFFu));
+                  f[2 * e + 1] += Act<DT>::to_f32((uint16_t)(rv[u][cbi][e] >> 16));
                 }
               }
               if (relu_all) {
@@ -295,11 +294,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
               uint32_t w[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) w[e] = pack2<DT>(f[2 * e], f[2 * e + 1]);
-              uint4* o = reinterpret_cast<uint4*>(y16 + pix0[u] * p.Cout + cb);
-              if (p.dbg != 2 || w[0] == 0x12345678u) {
-                o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                o[1] = make_uint4(w[4], w[5], w[6], w[7]);
-              }
+              if (p.dbg != 2 || w[0] == 0x12345678u) stg256(y16 + pix0[u] * p.Cout + cb, w);
             }
           }
         }

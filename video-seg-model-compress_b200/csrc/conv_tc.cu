@@ -529,9 +529,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           if (valid) {
             float r[16];
             if (p.has_res) {
-              const uint4* rp = reinterpret_cast<const uint4*>(res16 + pix0 * p.res_pitch + p.res_coff + cb);
-              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+              uint32_t rw[8];
+              ldg256_nc(res16 + pix0 * p.res_pitch + p.res_coff + cb, rw);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 r[2 * i] = Act<DT>::to_f32((uint16_t)(rw[i] & 0xFFFFu));
@@ -547,19 +546,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               o[i] = finish<DT>(__uint_as_float(v[i]), sync->scale[cb + i], sync->shift[cb + i], r[i],
                                 cb + i < p.relu_n);
             if (p.out_f32) {
-              float4* yp = reinterpret_cast<float4*>(y32 + off0 + cb);
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                yp[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+              for (int h = 0; h < 2; ++h) {
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(o[8 * h + i]);
+                stg256(y32 + off0 + cb + 8 * h, w);
+              }
             } else {
               uint32_t w[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                w[i] = (uint32_t)Act<DT>::from_f32(o[2 * i]) |
-                       ((uint32_t)Act<DT>::from_f32(o[2 * i + 1]) << 16);
-              uint4* yp = reinterpret_cast<uint4*>(y16 + off0 + cb);
-              yp[0] = make_uint4(w[0], w[1], w[2], w[3]);
-              yp[1] = make_uint4(w[4], w[5], w[6], w[7]);
+              for (int i = 0; i < 8; ++i) w[i] = pack2<DT>(o[2 * i], o[2 * i + 1]);
+              stg256(y16 + off0 + cb, w);
             }
           }
         }
