@@ -34,7 +34,7 @@ struct ConvParams {
   int ep_cw, ep_ch, ep_nch;   // chunk box (pixels wide x high), chunks per tile
   // ---- ROW variant of MODE_T (conv_tc.cu): input-row halo ring + weight-tile ring
   int row_mode, x_ring, w_ring, dbg;
-  int res_tma;                // MODE_T: residual chunks arrive in the staging ring by TMA (else through registers)
+  int ep_groups;              // MODE_T: epilogue groups of four warps (2 or 4)
   uint32_t main_bytes;
 };
 

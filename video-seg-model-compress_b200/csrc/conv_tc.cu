@@ -37,13 +37,14 @@
 
 namespace drnb200 {
 
-constexpr int kTcThreads = 352;   // TMA, MMA, 2 x 4 epilogue warps, epilogue-TMA warp (MODE_T); MODE_P uses warps 0-5
+__host__ __device__ constexpr int tc_threads(int ng) { return (3 + 4 * ng) * 32; }   // TMA, MMA, NG x 4 epilogue warps, epilogue-TMA warp (MODE_T); MODE_P uses warps 0-5
+constexpr int kTcThreads = tc_threads(2);
 constexpr int kMaxStages = 8;
 constexpr int MODE_T = 0;      // staged epilogue (16-bit output)
 constexpr int MODE_P = 1;
 constexpr int MODE_TD = 2;     // MODE_T with the direct (register -> global) epilogue: float32 output
 constexpr uint32_t kTmemCols = 512;
-constexpr int kEpRing = 4;     // staging buffers of the MODE_T epilogue
+constexpr int kMaxEpRing = 8;  // staging buffers of the MODE_T epilogue: 2 per epilogue group
 constexpr int kEpChunkPx = 32; // pixels per staged chunk (one tcgen05.ld.32x32b.x32 per warp)
 constexpr int kEpBufBytes = kEpChunkPx * 256;
 constexpr int kRowPx = 256;                       // ROW variant: output pixels per tile (one row segment)
@@ -61,9 +62,9 @@ struct __align__(16) TcSync {
   uint64_t xempty[kMaxXRing];
   uint64_t tfull[2];
   uint64_t tempty[2];
-  uint64_t rfull[kEpRing];    // staged epilogue: residual chunk landed in ring slot (TMA)
-  uint64_t sfree[kEpRing];    //                  ring slot may be overwritten (no-residual layers)
-  uint64_t sdone[kEpRing];    //                  the owning epilogue group finished the chunk
+  uint64_t rfull[kMaxEpRing];    // staged epilogue: residual chunk landed in ring slot (TMA)
+  uint64_t sfree[kMaxEpRing];    //                  ring slot may be overwritten (no-residual layers)
+  uint64_t sdone[kMaxEpRing];    //                  the owning epilogue group finished the chunk
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -94,12 +95,17 @@ __device__ __forceinline__ float finish(float acc, float sc, float sh, float res
   return relu ? fmaxf(v, 0.f) : v;
 }
 
-template <int MODE, int DT, bool ROW = false>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// NG = epilogue groups of four warps (MODE_T): 2 when the MMA loop dominates a tile, 4 for tiles with few live K-blocks
+// (fused downsample rows, 1x1 projections, heavily pruned layers), where finishing a 128 x 256 accumulator tile
+// (~7000 cycles with two groups: dependent 2-byte shared-memory accesses, ~6 cycles per instruction) is the bound.
+template <int MODE, int DT, bool ROW = false, int NG = 2>
+__global__ void __launch_bounds__(tc_threads(NG), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y,
                const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_x2,
                const ConvParams p) {
   static_assert(!ROW || MODE == MODE_T, "the ROW mainloop feeds the staged MODE_T epilogue");
+  static_assert(NG == 2 || (MODE == MODE_T && NG == 4), "four epilogue groups exist for the staged epilogue only");
+  constexpr int kEpRing = 2 * NG;             // = 2 * D below: D chunks being finished + D draining / being prepared
   extern __shared__ uint8_t smem_raw[];
   // tiles must sit on 1024-byte boundaries of the shared window (SWIZZLE_128B atom)
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -134,7 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&sync->tfull[a], 1);
-      mbar_init(&sync->tempty[a], MODE == MODE_T ? 8 : 4);  // one arrive per epilogue warp
+      mbar_init(&sync->tempty[a], MODE == MODE_T ? 4 * NG : 4);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -143,7 +149,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     tmem_relinquish();
   }
   if (MODE == MODE_P) {
-    for (int ch = threadIdx.x; ch < 256; ch += kTcThreads) {
+    for (int ch = threadIdx.x; ch < 256; ch += tc_threads(NG)) {
       sync->scale[ch] = ch < p.Cout ? __ldg(p.scale + ch) : 0.f;
       sync->shift[ch] = ch < p.Cout ? __ldg(p.shift + ch) : 0.f;
     }
@@ -314,9 +320,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
     if (MODE == MODE_T) {
       // ------------------------------------------------ staged: smem transpose + TMA load/store
-      // warps 2-9 = two groups of four warps taking alternate 32-pixel chunks (flat chunk index k: group k&1,
-      // ring slot k&3); warp 10 issues every residual load and output store and recycles the ring slots.
-      if (warp == 10) {
+      // warps 2 .. 2+4*NG-1 = NG groups of four warps taking 32-pixel chunks round-robin (flat chunk index k: group
+      // k % NG, ring slot k % (2*NG)); the last warp issues every residual load and output store and recycles the slots.
+      if (warp == 2 + 4 * NG) {
         // ---- epilogue TMA warp (warp-uniform loop; one elected lane issues and owns the bulk groups)
         const int nch = p.ep_nch;
         auto chunk_xy = [&](const TileCoord& c, int qq, int& cx, int& cy) {
@@ -324,7 +330,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           cx = c.ox0 + (j0 & (p.TW - 1));
           cy = c.oy0 + (j0 >> p.tw_shift);
         };
-        constexpr int D = 2;                       // loads run D chunks ahead of stores
+        constexpr int D = NG;                      // chunks in flight (prepared, not yet stored): one per group
         int hist_ot[D], hist_cx[D], hist_cy[D], hist_n[D];
         uint32_t k = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -333,21 +339,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             const uint32_t b = k & (kEpRing - 1);
             int cx, cy;
             chunk_xy(c, qq, cx, cy);
-            if (k >= (uint32_t)D) {                // finish chunk k-D: its group is done -> store it
-              const uint32_t kb = k - D, bb = kb & (kEpRing - 1);
-              mbar_wait(&sync->sdone[bb], (kb / kEpRing) & 1u);
-              if (elect_one()) {
-                tma_store_4d(&tmap_y, stg + bb * kEpBufBytes, hist_ot[kb % D] * 128, hist_cx[kb % D],
-                             hist_cy[kb % D], hist_n[kb % D]);
-                bulk_commit_group();
-              }
-              __syncwarp();
-            }
-            // prepare chunk k: ring slot b was last used by chunk k-4, whose store has been issued
-            // (k-4 <= k-1-D) and is complete once at most one newer store is still reading
+            // (A) prepare chunk k FIRST, so that the group that is finishing chunk k - D finds its next slot ready:
+            // ring slot b was last used by chunk k - kEpRing = k - 2D; the stores issued so far are those of chunks
+            // <= k - D - 1, D - 1 of them newer than that one, so it has drained once at most D - 1 are still reading
             if (elect_one()) {
-              bulk_wait_group_read<1>();
-              if (p.res_tma) {                      // residual chunk [32 px][128 couts] straight into the slot
+              bulk_wait_group_read<D - 1>();
+              if (p.has_res) {                      // residual chunk [32 px][128 couts] straight into the slot
                 mbar_arrive_expect_tx(&sync->rfull[b], kEpBufBytes);
                 tma_load_4d(&tmap_r, &sync->rfull[b], stg + b * kEpBufBytes, p.res_coff + c.ot * 128, cx, cy, c.n);
               } else {
@@ -355,6 +352,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               }
             }
             __syncwarp();
+            // (B) finish chunk k - D: its group is done -> store it
+            if (k >= (uint32_t)D) {
+              const uint32_t kb = k - D, bb = kb & (kEpRing - 1);
+              mbar_wait(&sync->sdone[bb], (kb / kEpRing) & 1u);
+              if (elect_one()) {
+                if (!(p.dbg & 8))
+                  tma_store_4d(&tmap_y, stg + bb * kEpBufBytes, hist_ot[kb % D] * 128, hist_cx[kb % D],
+                               hist_cy[kb % D], hist_n[kb % D]);
+                bulk_commit_group();
+              }
+              __syncwarp();
+            }
             hist_ot[k % D] = c.ot; hist_cx[k % D] = cx; hist_cy[k % D] = cy; hist_n[k % D] = c.n;
           }
         }
@@ -377,69 +386,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const int cl = q * 32 + lane;              // cout inside the 128-cout tile
         const int nch = p.ep_nch;
         uint32_t k0 = 0;                           // flat chunk index of the tile's first chunk
-        // residual chunk [32 px][128 couts] = 8 KB: four coalesced 16-byte loads per thread (two 256-byte
-        // pixel rows per warp instruction).  The loads run TWO of this group's chunks ahead of the chunk being
-        // finished (across tile boundaries: `pf` walks the same chunk sequence as the loops below), because under
-        // load an HBM round trip is longer than one chunk; the data is parked in the ring slot and then read back
-        // transposed (thread = cout).
-        const int tig = (warp - 2 - 4 * grp) * 32 + lane;      // thread index inside the group (0..127)
-        struct { int t, qq; uint32_t k0; TileCoord c; } pf;
-        pf.t = blockIdx.x; pf.k0 = 0; pf.qq = grp;
-        if (pf.t < p.total_tiles) pf.c = decode_tile(p, pf.t);
-        auto pf_settle = [&]() {                   // move to the next tile while this group owns no chunk of it
-          while (pf.t < p.total_tiles && pf.qq >= nch) {
-            pf.k0 += (uint32_t)nch;
-            pf.t += gridDim.x;
-            if (pf.t < p.total_tiles) { pf.c = decode_tile(p, pf.t); pf.qq = (int)((pf.k0 ^ (uint32_t)grp) & 1u); }
-          }
-        };
-        auto pf_load = [&](uint4 (&r)[4]) {        // load the chunk `pf` points at (zeros past the end), advance
-          pf_settle();
-          const bool ok = pf.t < p.total_tiles;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = u * 128 + tig, i = idx >> 4, part = idx & 15;
-            const int j = pf.qq * kEpChunkPx + i;
-            const int oy = pf.c.oy0 + (j >> p.tw_shift), ox = pf.c.ox0 + (j & (p.TW - 1));
-            r[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok && oy < p.OH && ox < p.OW && !(p.dbg & 4))
-              r[u] = __ldg(reinterpret_cast<const uint4*>(
-                  res16 + (((size_t)pf.c.n * p.OH + oy) * p.OW + ox) * p.res_pitch + p.res_coff + pf.c.ot * 128 +
-                  part * 8));
-          }
-          pf.qq += 2;
-        };
-        uint4 r0[4], r1[4], r2[4];
-        const bool res_regs = p.has_res && !p.res_tma;     // residual through registers (A/B knob DRNB200_RES=regs)
-        if (res_regs) { pf_load(r0); pf_load(r1); }
+        // the tile's decode and BN affine are fetched one tile ahead: on tiles with few live K-blocks this global
+        // round trip (plus the integer divisions of the decode) would otherwise sit on every warp's critical path
+        TileCoord c_next = decode_tile(p, blockIdx.x < p.total_tiles ? blockIdx.x : 0);
+        float sc_next = __ldg(p.scale + c_next.ot * 128 + cl), sh_next = __ldg(p.shift + c_next.ot * 128 + cl);
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-          const TileCoord c = decode_tile(p, t);
+          const TileCoord c = c_next;
+          const float sc = sc_next, sh = sh_next;
+          if (t + (int)gridDim.x < p.total_tiles) {
+            c_next = decode_tile(p, t + gridDim.x);
+            sc_next = __ldg(p.scale + c_next.ot * 128 + cl);
+            sh_next = __ldg(p.shift + c_next.ot * 128 + cl);
+          }
           const bool live = c.je > c.jb;
           const int co = c.ot * 128 + cl;
-          const float sc = __ldg(p.scale + co), sh = __ldg(p.shift + co);
           const int relu = co < p.relu_n;
-          int qq = (int)((k0 ^ (uint32_t)grp) & 1u);       // first chunk of this tile owned by this group
+          int qq = (int)(((uint32_t)grp - k0) & (uint32_t)(NG - 1));   // first chunk of this tile owned by this group
           if (live) {
             mbar_wait(&sync->tfull[acc], acc_phase);
             tc_fence_after();
           }
           const uint32_t t_addr = tmem_base + acc * 256u + ((uint32_t)(q * 32) << 16);
-          for (; qq < nch; qq += 2) {
+          for (; qq < nch; qq += NG) {
             const uint32_t k = k0 + (uint32_t)qq;
             const uint32_t b = k & (kEpRing - 1);
             uint8_t* buf = stg + b * kEpBufBytes;
-            if (res_regs) pf_load(r2);
-            if (p.res_tma) {
-              mbar_wait(&sync->rfull[b], (k / kEpRing) & 1u);   // slot drained AND the residual chunk has landed
-            } else {
-              mbar_wait(&sync->sfree[b], (k / kEpRing) & 1u);   // the slot's previous store has drained
-              if (res_regs) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  *reinterpret_cast<uint4*>(buf + (u * 128 + tig) * 16) = r0[u];
-                named_bar_sync(1 + grp, 128);         // the whole residual chunk is in the slot
-              }
-            }
+            // the slot's previous store has drained; with a residual, its chunk [32 px][128 couts] has landed (TMA)
+            if (p.has_res) mbar_wait(&sync->rfull[b], (k / kEpRing) & 1u);
+            else mbar_wait(&sync->sfree[b], (k / kEpRing) & 1u);
             uint32_t v[32];
             if (live) {
               tmem_ld32(t_addr + (uint32_t)(qq * kEpChunkPx), v);
@@ -449,18 +423,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               for (int i = 0; i < 32; ++i) v[i] = 0u;
             }
             uint16_t* col = reinterpret_cast<uint16_t*>(buf) + cl;   // [pixel][128 couts]
+            if (!(p.dbg & 16)) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float r = p.has_res ? Act<DT>::to_f32(col[i * 128]) : 0.f;
-              col[i * 128] = Act<DT>::from_f32(finish<DT>(__uint_as_float(v[i]), sc, sh, r, relu));
+              for (int i = 0; i < 32; ++i) {
+                const float r = p.has_res ? Act<DT>::to_f32(col[i * 128]) : 0.f;
+                col[i * 128] = Act<DT>::from_f32(finish<DT>(__uint_as_float(v[i]), sc, sh, r, relu));
+              }
             }
             fence_proxy_async_smem();              // st.shared -> visible to the TMA store
             __syncwarp();
             if (lane == 0) mbar_arrive(&sync->sdone[b]);
-            if (res_regs) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) { r0[u] = r1[u]; r1[u] = r2[u]; }
-            }
           }
           k0 += (uint32_t)nch;
           if (live) {                              // this warp has read all of its chunks of the accumulator
@@ -609,9 +581,9 @@ static int ilog2(int v) {
   return r;
 }
 
-template <int MODE, int DT, bool ROW = false>
+template <int MODE, int DT, bool ROW = false, int NG = 2>
 static int set_attr(size_t smem) {
-  DRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, DT, ROW>,
+  DRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, DT, ROW, NG>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return DRNB200_OK;
 }
@@ -662,22 +634,30 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   p.ep_nch = NT / kEpChunkPx;
   // ---- shared memory: as many stages as fit in 227 KB (also pins one CTA per SM: TMEM is taken whole)
   const size_t kMaxSmem = 232448;
-  const size_t fixed = 1024 + sizeof(TcSync) + (mode == MODE_T ? kEpRing * kEpBufBytes : 0);
+  // ---- epilogue groups (MODE_T): two by default.  A four-group instantiation exists (DRNB200_NG=4) and was measured:
+  //      once the store warp prepares a group's next slot BEFORE waiting for the chunk in flight, two groups finish
+  //      tiles as fast as four (layer-5/6 residual convs 0.129/0.249 -> 0.115/0.228 ms with either), and tiles with a
+  //      single live K-block stay at ~4700 cycles with no math and no stores at all (pipeline skeleton).
+  p.ep_groups = 2;
+  if (mode == MODE_T) {
+    static const char* env_ng = getenv("DRNB200_NG");        // A/B knob: force 2 or 4 epilogue groups
+    if (env_ng && (env_ng[0] == '2' || env_ng[0] == '4')) p.ep_groups = env_ng[0] - '0';
+  }
+  const size_t fixed = 1024 + sizeof(TcSync) + (mode == MODE_T ? 2 * p.ep_groups * kEpBufBytes : 0);
   int stages = (int)((kMaxSmem - fixed) / p.stage_bytes);
   stages = std::max(2, std::min(stages, kMaxStages));
   p.stages = stages;
   plan->smem_bytes = kMaxSmem;
   // ---- ROW variant: 3x3 stride-1 convs over 64-channel K-blocks whose tile is one 256-pixel row segment
   static const char* env_row = getenv("DRNB200_ROW");       // A/B knob: "0" keeps the per-tap pipeline
-  static const char* env_res = getenv("DRNB200_RES");        // A/B knob: "regs" = residual through registers
-  p.res_tma = (mode == MODE_T && p.has_res && !(env_res && env_res[0] == 'r')) ? 1 : 0;
   p.row_mode = 0;
   static const char* env_dbg = getenv("DRNB200_DBG");        // timing diagnostics of the ROW mainloop (results invalid):
-  p.dbg = env_dbg ? atoi(env_dbg) : 0;                       // 1 no weight loads, 2 no row loads, 4 no residual loads
+  p.dbg = env_dbg ? atoi(env_dbg) : 0;                       // 1 no weight loads, 2 no row loads, 4 no residual loads,
+                                                             // 8 no output stores, 16 no epilogue math / staging writes
   if (mode == MODE_T && p.taps == 9 && d.stride == 1 && p.tile_ci == 64 && d.dilation <= 4 && TW == kRowPx &&
       TH == 1 && !(env_row && env_row[0] == '0')) {
     static const char* env_ring = getenv("DRNB200_ROW_RING");   // "x,w" ring sizes for tuning
-    int xr = 3, wr = 5;
+    int xr = p.ep_groups == 4 ? 2 : 3, wr = 5;            // four groups: 64 KB of staging, shallower row ring
     if (env_ring && sscanf(env_ring, "%d,%d", &xr, &wr) != 2) { xr = 3; wr = 5; }
     xr = std::max(2, std::min(xr, kMaxXRing));
     wr = std::max(2, std::min(wr, kMaxStages));
@@ -686,9 +666,13 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
     p.main_bytes = (uint32_t)(xr * kRowBytes + wr * kRowWBytes);
   }
   int rc;
-  if (mode == MODE_T && p.row_mode)
-    rc = (d.act_dtype == DRNB200_BF16) ? set_attr<MODE_T, DRNB200_BF16, true>(plan->smem_bytes)
-                                       : set_attr<MODE_T, DRNB200_F16, true>(plan->smem_bytes);
+  const bool bf16 = d.act_dtype == DRNB200_BF16;
+  if (mode == MODE_T && p.row_mode && p.ep_groups == 4)
+    rc = bf16 ? set_attr<MODE_T, DRNB200_BF16, true, 4>(plan->smem_bytes) : set_attr<MODE_T, DRNB200_F16, true, 4>(plan->smem_bytes);
+  else if (mode == MODE_T && p.row_mode)
+    rc = bf16 ? set_attr<MODE_T, DRNB200_BF16, true>(plan->smem_bytes) : set_attr<MODE_T, DRNB200_F16, true>(plan->smem_bytes);
+  else if (mode == MODE_T && p.ep_groups == 4)
+    rc = bf16 ? set_attr<MODE_T, DRNB200_BF16, false, 4>(plan->smem_bytes) : set_attr<MODE_T, DRNB200_F16, false, 4>(plan->smem_bytes);
   else if (mode == MODE_T)
     rc = (d.act_dtype == DRNB200_BF16) ? set_attr<MODE_T, DRNB200_BF16>(plan->smem_bytes)
                                        : set_attr<MODE_T, DRNB200_F16>(plan->smem_bytes);
@@ -821,13 +805,21 @@ int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st) {
     if (bf) conv_tc_kernel<M, DRNB200_BF16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p); \
     else    conv_tc_kernel<M, DRNB200_F16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);  \
   } while (0)
-  if (plan->tc_mode == MODE_T && p.row_mode) {
-    if (bf) conv_tc_kernel<MODE_T, DRNB200_BF16, true><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);
-    else    conv_tc_kernel<MODE_T, DRNB200_F16, true><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);
+#define DRN_LAUNCH_T(ROWV, NGV)                                                                                       \
+  do {                                                                                                                \
+    const dim3 blk(tc_threads(NGV));                                                                                  \
+    if (bf) conv_tc_kernel<MODE_T, DRNB200_BF16, ROWV, NGV><<<grid, blk, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p); \
+    else    conv_tc_kernel<MODE_T, DRNB200_F16, ROWV, NGV><<<grid, blk, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);  \
+  } while (0)
+  if (plan->tc_mode == MODE_T && (p.row_mode || p.ep_groups == 4)) {
+    if (p.row_mode && p.ep_groups == 4) DRN_LAUNCH_T(true, 4);
+    else if (p.row_mode) DRN_LAUNCH_T(true, 2);
+    else DRN_LAUNCH_T(false, 4);
   } else if (plan->tc_mode == MODE_T) DRN_LAUNCH(MODE_T);
   else if (plan->tc_mode == MODE_TD) DRN_LAUNCH(MODE_TD);
   else DRN_LAUNCH(MODE_P);
 #undef DRN_LAUNCH
+#undef DRN_LAUNCH_T
   DRN_CUDA(cudaGetLastError());
   return DRNB200_OK;
 }
