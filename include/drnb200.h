@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRNB200_VERSION 102
+#define DRNB200_VERSION 103
 
 /* error codes */
 #define DRNB200_OK          0
@@ -176,6 +176,11 @@ int  drnb200_head_plan_create(drnb200_head_plan** out, int N, int h, int w, int 
 int  drnb200_head_forward(drnb200_head_plan* plan, const void* x_nhwc, uint8_t* labels,
                           float* seg_logits, float* logprob, void* stream);
 void drnb200_head_plan_destroy(drnb200_head_plan* plan);
+/* 1 when a labels-only drnb200_head_forward call (seg_logits == NULL, logprob == NULL) runs as ONE fused kernel
+ * (classifier GEMM on tcgen05 -> x8 bilinear upsample -> argmax -> packed label stores; needs C % 64 == 0,
+ * C <= 1024, classes <= 19); otherwise, and whenever logits or log-probs are requested, the classifier GEMM and
+ * the upsample run as two launches over a float32 [N,h,w,32] scratch. */
+int  drnb200_head_plan_fused(const drnb200_head_plan* plan);
 
 /* Confusion matrix accumulation: fast_hist (semantic_seg.py:293-296).
  * hist[label*classes + pred] += 1 for every pixel with 0 <= label < classes (255 = ignore falls out).

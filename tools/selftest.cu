@@ -348,8 +348,24 @@ static int run_head(int dt, int N, int h, int w) {
     }
   }
   printf("  head: seg bad=%zu label bad=%zu (near ties %zu) logprob bad=%zu\n", bad_seg, bad_lab, near_tie, bad_lp);
+  // labels-only call = the fused kernel (GEMM + upsample + argmax in one launch): byte-identical labels
+  size_t bad_fused = 0;
+  {
+    uint8_t* dl2; CK(cudaMalloc(&dl2, (size_t)N * H * W)); CK(cudaMemset(dl2, 0xEE, (size_t)N * H * W));
+    API(drnb200_head_forward(plan, dx, dl2, nullptr, nullptr, 0));
+    CK(cudaDeviceSynchronize());
+    std::vector<uint8_t> lab2 = dev_download(dl2, (size_t)N * H * W);
+    for (size_t i = 0; i < lab2.size(); ++i) bad_fused += lab2[i] != lab[i];
+    printf("  head: fused=%d labels-only call differs in %zu of %zu pixels\n", drnb200_head_plan_fused(plan), bad_fused, lab2.size());
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 5; ++i) API(drnb200_head_forward(plan, dx, dl2, nullptr, nullptr, 0));
+    CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("  head (labels only) time %.3f ms\n", ms / 5);
+  }
   drnb200_head_plan_destroy(plan);
-  const int ok = !bad_seg && !bad_lab && !bad_lp;
+  const int ok = !bad_seg && !bad_lab && !bad_lp && !bad_fused;
   printf("RESULT head_dt%d_%dx%d %s\n", dt, h, w, ok ? "PASS" : "FAIL");
   return ok ? 0 : 1;
 }

@@ -12,6 +12,9 @@
 //   => exactly two candidate rows: i0 = (y+4)>>3 with k0 = (y+4)&7, and i0-1 with k0+8; rows outside
 //      [0,h) are dropped without renormalisation (this is what differs from F.interpolate at borders).
 #include "conv_internal.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <cudaTypedefs.h>
 #include <new>
 
 struct drnb200_head_plan {
@@ -24,6 +27,9 @@ struct drnb200_head_plan {
   float* d_scale;    // [32] ones
   float* d_shift;    // [32] bias, zero padded
   float* d_logits;   // [N,h,w,32] fp32 scratch
+  int fused_ok;      // labels-only calls run head_fused_kernel
+  const void* fmap_ptr;
+  CUtensorMap fmap;  // [N,h,w,C] activations, box {64, 16, 8, 1}
 };
 
 namespace drnb200 {
@@ -49,6 +55,55 @@ __global__ void head_pad_kernel(const float* __restrict__ seg_w, const float* __
   }
   if (i < n_kb) kblk[i] = i;
   if (i == 0) { row_ptr[0] = 0; row_ptr[1] = n_kb; }
+}
+
+// ---- upsample core shared by up_argmax_kernel and head_fused_kernel.  Every product/sum is an explicitly rounded
+//      operation so that the two kernels produce bit-identical values (predict() == argmax of forward()).
+// vertical pass at low-res tile position `at` = &tile[ra][ca][0] (rows `row_pitch` floats apart, class pitch CP):
+// V0 = column j0, V1 = column j0-1, each = wy0 * row i0 + wy1 * row i0-1 (zeros were staged outside the map)
+template <int CLS_MAX>
+__device__ __forceinline__ void up_vertical(const float* at, int row_pitch, int ky, float (&V0)[CLS_MAX],
+                                            float (&V1)[CLS_MAX]) {
+  constexpr int CP = (CLS_MAX + 3) & ~3;
+  const float wy0 = up_w(ky), wy1 = up_w(ky + 8);
+#pragma unroll
+  for (int q = 0; q < CP / 4; ++q) {
+    const float4 a0 = *reinterpret_cast<const float4*>(at + 4 * q);
+    const float4 b0 = *reinterpret_cast<const float4*>(at - row_pitch + 4 * q);
+    const float4 a1 = *reinterpret_cast<const float4*>(at - CP + 4 * q);
+    const float4 b1 = *reinterpret_cast<const float4*>(at - row_pitch - CP + 4 * q);
+    const float a0v[4] = {a0.x, a0.y, a0.z, a0.w}, b0v[4] = {b0.x, b0.y, b0.z, b0.w};
+    const float a1v[4] = {a1.x, a1.y, a1.z, a1.w}, b1v[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (4 * q + e < CLS_MAX) {
+        V0[4 * q + e] = __fmaf_rn(wy1, b0v[e], __fmul_rn(wy0, a0v[e]));
+        V1[4 * q + e] = __fmaf_rn(wy1, b1v[e], __fmul_rn(wy0, a1v[e]));
+      }
+  }
+}
+// horizontal pass + argmax of 4 adjacent pixels (same 2x2 low-res neighbourhood): labels packed into 4 bytes;
+// strict > : the first maximum wins like torch.max
+template <int CLS_MAX>
+__device__ __forceinline__ uint32_t up_argmax4(const float (&V0)[CLS_MAX], const float (&V1)[CLS_MAX], int kx,
+                                               int classes, float (&best4)[4]) {
+  uint32_t packed = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float wx0 = up_w(kx + t), wx1 = up_w(kx + t + 8);
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < CLS_MAX; ++c) {
+      if (c < classes) {
+        const float v = __fmaf_rn(wx1, V1[c], __fmul_rn(wx0, V0[c]));
+        if (v > best) { best = v; arg = c; }
+      }
+    }
+    best4[t] = best;
+    packed |= (uint32_t)arg << (8 * t);
+  }
+  return packed;
 }
 
 // One CTA = a 64 x 16 block of full-resolution pixels; its 10 x 4 low-resolution neighbourhood of class
@@ -84,49 +139,22 @@ up_argmax_kernel(const float* __restrict__ L, int N, int h, int w, int classes,
   if (x0 >= W || y >= H) return;
 
   const int i0 = (y + 4) >> 3, ky = (y + 4) & 7;
-  const float wy0 = up_w(ky), wy1 = up_w(ky + 8);    // row i0 and row i0-1 (zeros were staged if outside)
   const int j0 = (x0 + 4) >> 3, kx = (x0 + 4) & 7;
   const int ra = i0 - ly0, ca = j0 - lx0;            // tile coordinates of (i0, j0); (i0-1, j0-1) = (ra-1, ca-1)
-
-  // vertical pass: V0 = column j0, V1 = column j0-1
   float V0[CLS_MAX], V1[CLS_MAX];
-#pragma unroll
-  for (int q = 0; q < CP / 4; ++q) {
-    const float4 a0 = *reinterpret_cast<const float4*>(&s_l[ra][ca][4 * q]);
-    const float4 b0 = *reinterpret_cast<const float4*>(&s_l[ra - 1][ca][4 * q]);
-    const float4 a1 = *reinterpret_cast<const float4*>(&s_l[ra][ca - 1][4 * q]);
-    const float4 b1 = *reinterpret_cast<const float4*>(&s_l[ra - 1][ca - 1][4 * q]);
-    const float a0v[4] = {a0.x, a0.y, a0.z, a0.w}, b0v[4] = {b0.x, b0.y, b0.z, b0.w};
-    const float a1v[4] = {a1.x, a1.y, a1.z, a1.w}, b1v[4] = {b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (4 * q + e < CLS_MAX) {
-        V0[4 * q + e] = wy0 * a0v[e] + wy1 * b0v[e];
-        V1[4 * q + e] = wy0 * a1v[e] + wy1 * b1v[e];
-      }
-  }
-
-  uint32_t packed = 0;
+  up_vertical<CLS_MAX>(&s_l[ra][ca][0], UP_LW * CP, ky, V0, V1);
+  float best4[4];
+  const uint32_t packed = up_argmax4<CLS_MAX>(V0, V1, kx, classes, best4);
   float lse[4];
+  if (logprob != nullptr) {
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const float wx0 = up_w(kx + t), wx1 = up_w(kx + t + 8);
-    float best = -INFINITY;
-    int arg = 0;
-#pragma unroll
-    for (int c = 0; c < CLS_MAX; ++c) {
-      if (c < classes) {
-        const float v = wx0 * V0[c] + wx1 * V1[c];
-        if (v > best) { best = v; arg = c; }  // strict > : first maximum wins (torch.max)
-      }
-    }
-    packed |= (uint32_t)arg << (8 * t);
-    if (logprob != nullptr) {
+    for (int t = 0; t < 4; ++t) {
+      const float wx0 = up_w(kx + t), wx1 = up_w(kx + t + 8);
       float s = 0.f;
 #pragma unroll
       for (int c = 0; c < CLS_MAX; ++c)
-        if (c < classes) s += expf(wx0 * V0[c] + wx1 * V1[c] - best);
-      lse[t] = best + logf(s);
+        if (c < classes) s += expf(__fmaf_rn(wx1, V1[c], __fmul_rn(wx0, V0[c])) - best4[t]);
+      lse[t] = best4[t] + logf(s);
     }
   }
   const size_t pix = ((size_t)n * H + y) * W + x0;
@@ -136,13 +164,196 @@ up_argmax_kernel(const float* __restrict__ L, int N, int h, int w, int classes,
     for (int c = 0; c < CLS_MAX; ++c) {
       if (c < classes) {
         float4 o;
-        o.x = up_w(kx + 0) * V0[c] + up_w(kx + 8) * V1[c] - lse[0];
-        o.y = up_w(kx + 1) * V0[c] + up_w(kx + 9) * V1[c] - lse[1];
-        o.z = up_w(kx + 2) * V0[c] + up_w(kx + 10) * V1[c] - lse[2];
-        o.w = up_w(kx + 3) * V0[c] + up_w(kx + 11) * V1[c] - lse[3];
+        o.x = __fmaf_rn(up_w(kx + 8), V1[c], __fmul_rn(up_w(kx + 0), V0[c])) - lse[0];
+        o.y = __fmaf_rn(up_w(kx + 9), V1[c], __fmul_rn(up_w(kx + 1), V0[c])) - lse[1];
+        o.z = __fmaf_rn(up_w(kx + 10), V1[c], __fmul_rn(up_w(kx + 2), V0[c])) - lse[2];
+        o.w = __fmaf_rn(up_w(kx + 11), V1[c], __fmul_rn(up_w(kx + 3), V0[c])) - lse[3];
         *reinterpret_cast<float4*>(logprob + (((size_t)n * classes + c) * H + y) * W + x0) = o;
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// head_fused_kernel — (c) as ONE kernel: classifier GEMM (tcgen05, TMEM) -> low-res class logits in shared memory
+// -> fixed-bilinear x8 upsample -> argmax -> packed label stores.  Nothing but the label map is written.
+// Persistent CTAs; tile = 112 x 48 output pixels = the 16 x 8 low-resolution neighbourhood (14 x 6 interior + the
+// one-pixel apron the transposed conv reaches into) = exactly the 128 rows of one UMMA M tile.
+//   warp 0      TMA: per tile C/64 K-blocks, box {64 ch, 16, 8} (out-of-map pixels arrive as zeros)
+//   warp 1      MMA: D[128 px][32 classes] += A[128 x 64] * W[32 x 64]^T, classifier weights resident in smem
+//   warps 2-5   TMEM -> + bias (0 for pixels outside the map: the transposed conv pads with zeros, not with the
+//               bias) -> shared-memory logits [128 px][20]
+//   warps 6-17  upsample + argmax, one thread = 4 adjacent pixels, 4 labels per 32-bit store (rows of 112 bytes)
+constexpr int HF_LW = 16, HF_LH = 8;                  // low-res tile incl. apron
+constexpr int HF_OW = (HF_LW - 2) * 8, HF_OH = (HF_LH - 2) * 8;   // 112 x 48 output pixels
+constexpr int HF_STAGES = 6, HF_ACC = 4, HF_LBUF = 2;
+constexpr int HF_UP_WARPS = 12;
+constexpr int HF_THREADS = (6 + HF_UP_WARPS) * 32;
+constexpr int HF_CP = 20;                             // class pitch of the staged logits (19 classes, float4 reads)
+constexpr int HF_MAX_KB = 16;                         // C <= 1024
+
+struct HeadFusedParams {
+  const uint8_t* w_packed;     // C/64 tiles of 32 x 64 (128-byte rows, SWIZZLE_128B)
+  const float* bias;           // [32], zero padded
+  uint8_t* labels;             // [N, 8h, 8w]
+  int N, h, w, n_kb, classes, tiles_x, tiles_y, total_tiles;
+  uint32_t idesc;
+};
+
+struct __align__(16) HFSync {
+  alignas(16) float logits[HF_LBUF][HF_LW * HF_LH][HF_CP];
+  alignas(16) float bias[32];
+  uint64_t full[HF_STAGES], empty[HF_STAGES], tfull[HF_ACC], tempty[HF_ACC], lfull[HF_LBUF], lempty[HF_LBUF], wfull;
+  uint32_t tmem_base, pad;
+};
+
+template <int DT>
+__global__ void __launch_bounds__(HF_THREADS, 1)
+head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* ring = smem;                                   // HF_STAGES x 16 KB: [128 px][64 ch] 16-bit
+  uint8_t* wsm = smem + HF_STAGES * 16384;                // n_kb x 4 KB
+  __shared__ HFSync sync_s;
+  HFSync* sync = &sync_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < HF_STAGES; ++i) { mbar_init(&sync->full[i], 1); mbar_init(&sync->empty[i], 1); }
+    for (int i = 0; i < HF_ACC; ++i) { mbar_init(&sync->tfull[i], 1); mbar_init(&sync->tempty[i], 4); }
+    for (int i = 0; i < HF_LBUF; ++i) { mbar_init(&sync->lfull[i], 4); mbar_init(&sync->lempty[i], HF_UP_WARPS); }
+    mbar_init(&sync->wfull, 1);
+    mbar_fence_init();
+  }
+  if (threadIdx.x < 32) sync->bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+  if (warp == 1) {
+    tmem_alloc(&sync->tmem_base, HF_ACC * 32);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sync->tmem_base;
+  const int tiles_per_frame = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer (warp-uniform loop)
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&sync->wfull, (uint32_t)p.n_kb * 4096u);
+      bulk_load(p.w_packed, &sync->wfull, wsm, (uint32_t)p.n_kb * 4096u);
+    }
+    uint32_t s = 0, ph = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int n = t / tiles_per_frame, r = t - n * tiles_per_frame;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int lx0 = tx * (HF_LW - 2) - 1, ly0 = ty * (HF_LH - 2) - 1;
+      for (int kb = 0; kb < p.n_kb; ++kb) {
+        mbar_wait(&sync->empty[s], ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sync->full[s], 16384u);
+          tma_load_4d(&tmap_x, &sync->full[s], ring + s * 16384, kb * 64, lx0, ly0, n);
+        }
+        __syncwarp();
+        if (++s == HF_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer (warp-uniform loop)
+    mbar_wait(&sync->wfull, 0);
+    const uint64_t d_hi = umma_smem_desc(0u, 128);
+    const uint32_t w16 = smem_u32(wsm) >> 4, r16 = smem_u32(ring) >> 4;
+    uint32_t s = 0, ph = 0;
+    int i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      const int acc = i % HF_ACC;
+      mbar_wait(&sync->tempty[acc], ((uint32_t)(i / HF_ACC) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * 32u;
+      for (int kb = 0; kb < p.n_kb; ++kb) {
+        mbar_wait(&sync->full[s], ph);
+        tc_fence_after();
+        const uint32_t a16 = r16 + s * (16384u >> 4), b16 = w16 + (uint32_t)kb * (4096u >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(d_tmem, d_hi | (uint64_t)(a16 + 2u * ks), d_hi | (uint64_t)(b16 + 2u * ks), p.idesc,
+                     (kb > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&sync->empty[s]);
+        }
+        __syncwarp();
+        if (++s == HF_STAGES) { s = 0; ph ^= 1u; }
+      }
+      if (elect_one()) umma_commit(&sync->tfull[acc]);
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ================================================================= logits: TMEM -> +bias -> shared memory
+    const int q = warp & 3, m = q * 32 + lane;          // TMEM lane = low-res pixel (row m / 16, column m % 16)
+    int i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      const int acc = i % HF_ACC, lb = i % HF_LBUF;
+      const int n = t / tiles_per_frame, r = t - n * tiles_per_frame;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int lx = tx * (HF_LW - 2) - 1 + (m & (HF_LW - 1)), ly = ty * (HF_LH - 2) - 1 + (m >> 4);
+      const bool inside = lx >= 0 && lx < p.w && ly >= 0 && ly < p.h;
+      mbar_wait(&sync->tfull[acc], (uint32_t)(i / HF_ACC) & 1u);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (uint32_t)acc * 32u + ((uint32_t)(q * 32) << 16), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sync->tempty[acc]);
+      mbar_wait(&sync->lempty[lb], ((uint32_t)(i / HF_LBUF) & 1u) ^ 1u);
+      float* dst = &sync->logits[lb][m][0];
+#pragma unroll
+      for (int c4 = 0; c4 < HF_CP / 4; ++c4) {
+        float4 o;
+        o.x = inside ? __fadd_rn(__uint_as_float(v[4 * c4]), sync->bias[4 * c4]) : 0.f;
+        o.y = inside ? __fadd_rn(__uint_as_float(v[4 * c4 + 1]), sync->bias[4 * c4 + 1]) : 0.f;
+        o.z = inside ? __fadd_rn(__uint_as_float(v[4 * c4 + 2]), sync->bias[4 * c4 + 2]) : 0.f;
+        o.w = inside ? __fadd_rn(__uint_as_float(v[4 * c4 + 3]), sync->bias[4 * c4 + 3]) : 0.f;
+        *reinterpret_cast<float4*>(dst + 4 * c4) = o;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sync->lfull[lb]);
+    }
+  } else {
+    // ================================================================= upsample + argmax
+    const int ut = (warp - 6) * 32 + lane;              // 0 .. 383
+    const int H = 8 * p.h, W = 8 * p.w;
+    constexpr int ITEMS = HF_OH * (HF_OW / 4);          // 48 rows x 28 quads
+    int i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      const int lb = i % HF_LBUF;
+      const int n = t / tiles_per_frame, r = t - n * tiles_per_frame;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int X0 = tx * HF_OW, Y0 = ty * HF_OH;
+      const int lx0 = tx * (HF_LW - 2) - 1, ly0 = ty * (HF_LH - 2) - 1;
+      mbar_wait(&sync->lfull[lb], (uint32_t)(i / HF_LBUF) & 1u);
+      const float* tile = &sync->logits[lb][0][0];
+      for (int it = ut; it < ITEMS; it += HF_UP_WARPS * 32) {
+        const int yy = it / (HF_OW / 4), xq = it - yy * (HF_OW / 4);
+        const int y = Y0 + yy, x0 = X0 + 4 * xq;
+        if (y < H && x0 < W) {
+          const int i0 = (y + 4) >> 3, ky = (y + 4) & 7, j0 = (x0 + 4) >> 3, kx = (x0 + 4) & 7;
+          const int ra = i0 - ly0, ca = j0 - lx0;
+          float V0[19], V1[19], best4[4];
+          up_vertical<19>(tile + (ra * HF_LW + ca) * HF_CP, HF_LW * HF_CP, ky, V0, V1);
+          const uint32_t packed = up_argmax4<19>(V0, V1, kx, p.classes, best4);
+          *reinterpret_cast<uint32_t*>(p.labels + ((size_t)n * H + y) * W + x0) = packed;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sync->lempty[lb]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, HF_ACC * 32);
   }
 }
 
@@ -213,14 +424,73 @@ extern "C" int drnb200_head_plan_create(drnb200_head_plan** out, int N, int h, i
                                   p->d_shift);
   }
   if (rc != DRNB200_OK) { drnb200_head_plan_destroy(p); return rc; }
+  static const char* env_hf = getenv("DRNB200_HEAD");      // A/B knob: "split" keeps GEMM + upsample as two launches
+  p->fused_ok = (tile_ci == 64 && n_kb <= HF_MAX_KB && classes <= 19 && !(env_hf && env_hf[0] == 's')) ? 1 : 0;
+  p->fmap_ptr = nullptr;
   *out = p;
   return DRNB200_OK;
 }
+
+static int head_fused_launch(drnb200_head_plan* plan, const void* x, uint8_t* labels, cudaStream_t st) {
+  if (plan->fmap_ptr != x) {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+      void* sym = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+          qres != cudaDriverEntryPointSuccess) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return DRNB200_E_CUDA;
+      }
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(sym);
+    }
+    cuuint64_t gdim[4] = {(cuuint64_t)plan->C, (cuuint64_t)plan->w, (cuuint64_t)plan->h, (cuuint64_t)plan->N};
+    cuuint64_t gstr[3] = {(cuuint64_t)plan->C * 2, (cuuint64_t)plan->w * plan->C * 2,
+                          (cuuint64_t)plan->h * plan->w * plan->C * 2};
+    cuuint32_t box[4] = {64, HF_LW, HF_LH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&plan->fmap, plan->act_dtype == DRNB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                    4, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(head) failed with CUresult %d", (int)r); return DRNB200_E_CUDA; }
+    plan->fmap_ptr = x;
+  }
+  HeadFusedParams p{};
+  p.w_packed = reinterpret_cast<const uint8_t*>(plan->d_wpacked);
+  p.bias = plan->d_shift; p.labels = labels;
+  p.N = plan->N; p.h = plan->h; p.w = plan->w; p.n_kb = plan->C / 64; p.classes = plan->classes;
+  p.tiles_x = (8 * plan->w + HF_OW - 1) / HF_OW;
+  p.tiles_y = (8 * plan->h + HF_OH - 1) / HF_OH;
+  p.total_tiles = plan->N * p.tiles_x * p.tiles_y;
+  p.idesc = umma_idesc_f16(128, HEAD_CP, plan->act_dtype);
+  const size_t smem = 1024 + HF_STAGES * 16384 + (size_t)p.n_kb * 4096;
+  constexpr size_t kHfMaxSmem = 1024 + HF_STAGES * 16384 + (size_t)HF_MAX_KB * 4096;
+  int dev = 0, sms = 148;
+  DRN_CUDA(cudaGetDevice(&dev));
+  DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = std::min(p.total_tiles, sms);
+  if (grid == 0) return DRNB200_OK;
+  static bool attr[2] = {false, false};
+  if (plan->act_dtype == DRNB200_BF16) {
+    if (!attr[0]) { DRN_CUDA(cudaFuncSetAttribute(head_fused_kernel<DRNB200_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHfMaxSmem)); attr[0] = true; }
+    head_fused_kernel<DRNB200_BF16><<<grid, HF_THREADS, smem, st>>>(plan->fmap, p);
+  } else {
+    if (!attr[1]) { DRN_CUDA(cudaFuncSetAttribute(head_fused_kernel<DRNB200_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHfMaxSmem)); attr[1] = true; }
+    head_fused_kernel<DRNB200_F16><<<grid, HF_THREADS, smem, st>>>(plan->fmap, p);
+  }
+  DRN_CUDA(cudaGetLastError());
+  return DRNB200_OK;
+}
+
+extern "C" int drnb200_head_plan_fused(const drnb200_head_plan* plan) { return (plan && plan->fused_ok) ? 1 : 0; }
 
 extern "C" int drnb200_head_forward(drnb200_head_plan* plan, const void* x_nhwc, uint8_t* labels,
                                     float* seg_logits, float* logprob, void* stream) {
   DRN_REQUIRE(plan && x_nhwc, "head_forward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (labels && !seg_logits && !logprob && plan->fused_ok)      // the fast path: one kernel, labels only
+    return head_fused_launch(plan, x_nhwc, labels, st);
   int rc = drnb200_conv_forward(plan->conv, x_nhwc, nullptr, plan->d_logits, stream);
   if (rc) return rc;
   if (labels || logprob) {

@@ -582,7 +582,10 @@ class Engine:
         with timed("head"):
             ffi.check(lib.drnb200_head_forward(hp, ffi.ptr(outs[last]), ffi.ptr(labels), ffi.ptr(seg),
                                                ffi.ptr(logprob), st), "head_forward")
-        launches += 1 + int(want_labels or want_logprob) + int(want_seg)
+        if want_labels and not want_logprob and not want_seg and lib.drnb200_head_plan_fused(hp):
+            launches += 1                    # classifier + upsample + argmax in one kernel
+        else:
+            launches += 1 + int(want_labels or want_logprob) + int(want_seg)
         self.launches_per_forward = launches
         return labels, logprob, seg
 
