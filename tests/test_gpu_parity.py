@@ -238,18 +238,24 @@ def test_forward_against_golden_fixture(name, arch, act):
     assert np.abs(sample - fx["logprob_sample"]).max() <= tol * np.abs(fx["seg"]).max() * 1.5
 
 
-def _gate_case(arch, h, w, n, pruned, act, seed):
+def _gate_case(arch, h, w, n, pruned, act, seed, cfg=None):
     shapes = load_keys(arch)
     sd = recipe.make_state_dict(shapes, seed=seed)
     model = drnb200.DRNSeg(arch, 19, pretrained=False, act_dtype=act)
     model.load_state_dict(sd, strict=False)
     masks = None
     if pruned:
-        import json, tempfile, os
+        import contextlib, io, json, tempfile, os
+        cfg = cfg if cfg is not None else recipe.block_pruner_config(shapes, 0.75)
         with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
-            json.dump(recipe.block_pruner_config(shapes, 0.75), fh)
+            json.dump(cfg, fh)
         pruner = drnb200.pruners.make_pruner(fh.name, on_gpu=False)
-        pruner.generate_masks(model, is_static=False)
+        np.random.seed(seed)                       # srmbrep patterns draw from numpy's global RNG
+        with contextlib.redirect_stdout(io.StringIO()):      # RmbPruner prints progress like the reference
+            if cfg["pruner_type"] == "rmb":
+                pruner.generate_masks(model)       # RmbPruner.generate_masks has no is_static (RmbPruner.py:111)
+            else:
+                pruner.generate_masks(model, is_static=False)
         os.unlink(fh.name)
         masks = pruner.mask_dict
         sd = recipe.sparse_reinit(sd, masks, seed=seed)
@@ -286,6 +292,67 @@ def test_parity_gates_drn_d_22(pruned):
     assert abs(meter.miou() - ref_miou) <= 0.1
 
 
+def _check_config_case(model, sd, x, min_agree, tag):
+    """logits gate + label agreement (all pixels, and pixels whose fp32 margin exceeds the logit tolerance)"""
+    ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
+    ref_lab = torch.max(ref_lp, 1)[1]
+    with torch.no_grad():
+        lp, seg = model(x.to(dev()))
+        lab = model.predict(x.to(dev())).cpu().long()
+    assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL
+    assert torch.equal(torch.max(lp, 1)[1].cpu(), lab)
+    top2 = ref_lp.topk(2, dim=1)[0]
+    confident = (top2[:, 0] - top2[:, 1]) > LOGIT_RTOL * ref_seg.abs().max()
+    agree_all = (lab == ref_lab).float().mean().item()
+    agree_conf = (lab == ref_lab)[confident].float().mean().item()
+    print("%s: logits rel err %.2e, argmax agreement %.5f (confident %.1f %% of pixels: %.5f), %d classes" % (
+        tag, rel_err(seg.cpu(), ref_seg), agree_all, 100 * confident.float().mean().item(), agree_conf,
+        len(ref_lab.unique())))
+    assert agree_conf >= LABEL_AGREE and agree_all >= min_agree
+    return lab, ref_lab
+
+
+def test_config3_drn_d_38_rmb_masks():
+    """BASELINE config 3: DRN-D-38 with RmbPruner masks (row-wise outer sparsity 0.5 + blocklets)"""
+    shapes = load_keys("drn_d_38")
+    model, sd, x = _gate_case("drn_d_38", 128, 256, 2, True, "fp16", seed=21,
+                              cfg=recipe.rmb_pruner_config(shapes, 0.5))
+    _check_config_case(model, sd, x, 0.995, "config 3 (D-38, rmb)")
+    dense, live, tile = model.engine().mac_counts(1, 128, 256)
+    assert live < 0.2 * dense and tile < 0.62 * dense        # dead outer blocks are skipped as tiles
+
+
+def test_config4_drn_d_54_srmbrep_masks():
+    """BASELINE config 4: DRN-D-54 (Bottleneck) with per-layer srmbrep masks shaped like optimal_configs/drn_d_54:
+    sparsity is finer than a tile, so every tile stays live and the result must still be exact in the mask"""
+    shapes = load_keys("drn_d_54")
+    model, sd, x = _gate_case("drn_d_54", 128, 256, 1, True, "fp16", seed=22,
+                              cfg=recipe.srmbrep_config(shapes, 0.75))
+    _check_config_case(model, sd, x, 0.995, "config 4 (D-54, srmbrep)")
+    dense, live, tile = model.engine().mac_counts(1, 128, 256)
+    assert live < 0.3 * dense and tile > 0.95 * dense
+
+
+def test_config5_drn_d_22_unstructured_90():
+    """BASELINE config 5: torch.nn.utils.prune.l1_unstructured(amount=0.9) on EVERY Conv2d incl. stem and seg
+    (semseg_unstructured.py:769-774); masks come from the weight_mask buffers, compacted to block tiles"""
+    import torch.nn.utils.prune as prune
+    model, sd, x = _gate_case("drn_d_22", 128, 256, 1, False, "fp16", seed=23)
+    for _, module in model.named_modules():
+        if isinstance(module, torch.nn.Conv2d):
+            prune.l1_unstructured(module, name="weight", amount=0.9)
+    eff = drnb200.checkpoint.normalize_state_dict(model.state_dict())
+    eff = eff[0] if isinstance(eff, tuple) else eff
+    for k in sd:
+        if k in eff and k.endswith(".weight") and sd[k].dim() == 4 and not k.startswith("up."):
+            nz = float((eff[k] != 0).float().mean())
+            assert abs(nz - 0.1) < 0.01, (k, nz)
+            sd[k] = eff[k].detach().cpu().clone()
+    _check_config_case(model, sd, x, 0.99, "config 5 (D-22, unstructured 90 %)")
+    dense, live, tile = model.engine().mac_counts(1, 128, 256)
+    assert live < 0.11 * dense and tile > 0.9 * dense        # unstructured zeros leave (almost) every tile live
+
+
 def test_bf16_storage_reported_separately():
     """bf16 activation storage (north_star's nominal layout): logits gate holds; the label agreement is
     reported, and must hold on pixels whose fp32 top-1/top-2 margin exceeds the logit tolerance"""
@@ -315,7 +382,7 @@ def test_per_layer_outputs_track_the_oracle():
     # run the engine layer by layer through its public ops (same launches as run())
     with torch.no_grad():
         model.predict(x.to(dev()))
-    assert eng.launches_per_forward == 1 + len(eng.ops) + 2
+    assert eng.launches_per_forward == 1 + len(eng.ops) + 1      # stem + convs + ONE fused head launch
     dense, live, tile = eng.mac_counts(1, 64, 128)
     assert live < dense and live <= tile <= dense
     assert abs(live / dense - 0.27) < 0.03          # 75 % of the 24 prunable layers + dense stem/seg

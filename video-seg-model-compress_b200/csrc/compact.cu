@@ -9,26 +9,55 @@
 
 namespace drnb200 {
 
-// grid = (n_cib, n_ot).  One CTA scans the tile_o x (tile_ci*taps) slab of the mask that belongs to
-// (ot, cib); along a mask row the slab is contiguous, so consecutive threads read consecutive floats.
-__global__ void compact_flags_kernel(const float* __restrict__ mask, int I, int taps, int tile_o,
-                                     int tile_ci, int n_kb, uint8_t* __restrict__ live) {
-  __shared__ int flags[64];
-  const int cib = blockIdx.x, ot = blockIdx.y;
-  if (threadIdx.x < 64) flags[threadIdx.x] = 0;
+// grid = (n_cib, O / rows_per_cta).  One CTA scans `rows_per_cta` rows of the tile_o x (tile_ci*taps) slab of the
+// mask that belongs to (ot, cib); along a mask row the slab is contiguous, so consecutive threads read consecutive
+// floats (16-byte loads when the slab is 16-byte aligned).  The host picks rows_per_cta so that a 512x512x3x3 mask
+// (9.4 MB) is spread over >= 4 CTAs per SM: the pass is HBM-bound instead of latency-bound on n_cib*n_ot CTAs.
+// `live` is zeroed by the caller; CTAs of the same (ot, cib) only ever store 1 (no atomics needed).
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+compact_flags_kernel(const float* __restrict__ mask, int I, int taps, int tile_o, int tile_ci, int n_kb,
+                     int rows_per_cta, uint8_t* __restrict__ live) {
+  __shared__ unsigned int sflags[2];   // bit t of the 64-bit pair = tap t has a non-zero element
+  const int cib = blockIdx.x, r0 = blockIdx.y * rows_per_cta, ot = r0 / tile_o;
+  if (threadIdx.x < 2) sflags[threadIdx.x] = 0u;
   __syncthreads();
   const int slab_w = tile_ci * taps;  // contiguous floats per row
   const size_t row_len = (size_t)I * taps;
-  const float* base = mask + (size_t)ot * tile_o * row_len + (size_t)cib * slab_w;
-  const int total = tile_o * slab_w;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    int r = idx / slab_w, c = idx - r * slab_w;
-    float v = __ldg(base + (size_t)r * row_len + c);
-    if (v != 0.0f) flags[c % taps] = 1;  // benign race: every writer stores 1
+  const float* base = mask + (size_t)r0 * row_len + (size_t)cib * slab_w;
+  unsigned long long f = 0ull;
+  if (VEC4) {
+    const int qw = slab_w >> 2, total = rows_per_cta * qw;
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int r = idx / qw, q = idx - r * qw;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)r * row_len) + q);
+      const int t0 = (q << 2) % taps;
+      int t1 = t0 + 1; t1 = t1 == taps ? 0 : t1;
+      int t2 = t1 + 1; t2 = t2 == taps ? 0 : t2;
+      int t3 = t2 + 1; t3 = t3 == taps ? 0 : t3;
+      if (v.x != 0.0f) f |= 1ull << t0;
+      if (v.y != 0.0f) f |= 1ull << t1;
+      if (v.z != 0.0f) f |= 1ull << t2;
+      if (v.w != 0.0f) f |= 1ull << t3;
+    }
+  } else {
+    const int total = rows_per_cta * slab_w;
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int r = idx / slab_w, c = idx - r * slab_w;
+      if (__ldg(base + (size_t)r * row_len + c) != 0.0f) f |= 1ull << (c % taps);
+    }
+  }
+  const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)f);
+  const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(f >> 32));
+  if ((threadIdx.x & 31) == 0) {
+    if (lo) atomicOr(&sflags[0], lo);
+    if (hi) atomicOr(&sflags[1], hi);
   }
   __syncthreads();
-  if (threadIdx.x < taps)
-    live[(size_t)ot * n_kb + cib * taps + threadIdx.x] = (uint8_t)flags[threadIdx.x];
+  if (threadIdx.x < taps && ((sflags[threadIdx.x >> 5] >> (threadIdx.x & 31)) & 1u))
+    live[(size_t)ot * n_kb + cib * taps + threadIdx.x] = (uint8_t)1;
 }
 
 // single CTA: counts per output tile, exclusive scan, ordered fill of kblk.
@@ -101,8 +130,17 @@ extern "C" int drnb200_compact_mask(const float* mask_oihw, int O, int I, int kh
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* live = nullptr;
   DRN_CUDA(cudaMallocAsync((void**)&live, (size_t)n_ot * n_kb, st));
-  compact_flags_kernel<<<dim3(n_cib, n_ot), 256, 0, st>>>(mask_oihw, I, taps, tile_o, tile_ci, n_kb,
-                                                         live);
+  DRN_CUDA(cudaMemsetAsync(live, 0, (size_t)n_ot * n_kb, st));
+  int rows_per_cta = tile_o;       // halve while the grid has fewer than 4 CTAs per SM (148 SMs)
+  while (rows_per_cta % 2 == 0 && (long long)n_cib * (O / rows_per_cta) < 4 * 148) rows_per_cta /= 2;
+  DRN_REQUIRE(O / rows_per_cta <= 65535, "compact_mask: grid too large (O=%d)", O);
+  const dim3 grid(n_cib, O / rows_per_cta);
+  const bool vec4 = ((tile_ci * taps) % 4 == 0) && (((size_t)I * taps) % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(mask_oihw) & 15u) == 0);
+  if (vec4)
+    compact_flags_kernel<true><<<grid, 256, 0, st>>>(mask_oihw, I, taps, tile_o, tile_ci, n_kb, rows_per_cta, live);
+  else
+    compact_flags_kernel<false><<<grid, 256, 0, st>>>(mask_oihw, I, taps, tile_o, tile_ci, n_kb, rows_per_cta, live);
   compact_scan_kernel<<<1, 256, (n_ot + 1) * sizeof(int32_t), st>>>(live, n_ot, n_kb, row_ptr, kblk,
                                                                    n_live);
   cudaError_t e = cudaGetLastError();

@@ -36,6 +36,17 @@ def _pick_tiles(cin, cout):
     return tile_o, tile_ci
 
 
+
+def _effective_weight(conv):
+    """(weight tensor, version key) of a dense-path conv (stem, seg).  Under torch.nn.utils.prune the module's
+    `weight` attribute is only refreshed by the forward pre-hook (semseg_unstructured.py:770-773 prunes the stem
+    and `seg` too), which this path never runs: recompute `weight_orig * weight_mask` like the hook does."""
+    if hasattr(conv, "weight_orig") and hasattr(conv, "weight_mask"):
+        w, m = conv.weight_orig.detach(), conv.weight_mask.detach()
+        return w * m.to(w.dtype), ("pruned", conv.weight_orig._version, conv.weight_mask._version)
+    return conv.weight.detach(), conv.weight._version
+
+
 class ConvLayer:
     """one conv (+BN) (+residual) (+ReLU) of the network and its derived device-side cache"""
 
@@ -395,7 +406,8 @@ class Engine:
         for op in self.ops:
             rebuilt += bool(op.refresh(self.mask_dict, self.act_dtype, device))
         conv, bn, _ = self.stem
-        ver = (conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version,
+        stem_w, stem_wver = _effective_weight(conv)
+        ver = (stem_wver, bn.weight._version, bn.bias._version, bn.running_mean._version,
                bn.running_var._version, str(device))
         if getattr(self, "_stem_version", None) != ver:
             inv = torch.rsqrt(bn.running_var.detach().to(device, torch.float32) + bn.eps)
@@ -403,17 +415,18 @@ class Engine:
             self.stem_shift = (bn.bias.detach().to(device, torch.float32)
                                - bn.running_mean.detach().to(device, torch.float32) * self.stem_scale
                                ).contiguous()
-            self.stem_w = conv.weight.detach().to(device, torch.float32).contiguous()
+            self.stem_w = stem_w.to(device, torch.float32).contiguous()
             self._stem_version = ver
             self._drop_stem_plans()
         seg = self.m.seg
-        hver = (seg.weight._version, seg.bias._version, self.act_dtype, str(device))
+        seg_w, seg_wver = _effective_weight(seg)
+        hver = (seg_wver, seg.bias._version, self.act_dtype, str(device))
         if self.head_version != hver:
             lib = ffi.lib()
             for p in self.head_plans.values():
                 lib.drnb200_head_plan_destroy(p)
             self.head_plans = {}
-            self.seg_w = seg.weight.detach().to(device, torch.float32).reshape(seg.out_channels, -1).contiguous()
+            self.seg_w = seg_w.to(device, torch.float32).reshape(seg.out_channels, -1).contiguous()
             self.seg_b = seg.bias.detach().to(device, torch.float32).contiguous()
             self.head_version = hver
         return rebuilt

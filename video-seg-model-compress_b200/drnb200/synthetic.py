@@ -128,6 +128,50 @@ def block_pruner_config(shapes, sparsity=0.75, path=None):
     return cfg
 
 
+def rmb_pruner_config(shapes, global_sp=0.5, path=None):
+    """BASELINE config 3: RmbPruner JSON (pruners/RmbPruner.py:90-107).  Outer block = min(128, Cout/2) rows x
+    (min(64, Cin/2) channels * kh*kw) matricised columns with row-wise outer sparsity `global_sp` (tile-aligned,
+    so the kernels skip the dead outer blocks); inside a live block one blocklet of 8 rows x 1 channel
+    (kh*kw columns) per blocklet-row is kept `count` times = a quarter of the block's channels."""
+    groups = collections.OrderedDict()
+    for key in prunable_keys(shapes):
+        o, i, kh, kw = shapes[key]
+        bh, bc = min(128, o // 2), min(64, i // 2)
+        groups.setdefault((bh, bc * kh * kw, kh * kw, max(1, bc // 4)), []).append(key)
+    cfg = {"pruner_type": "rmb", "configs": [
+        {"layer_set": keys, "global_bh": bh, "global_bw": bw, "global_sp": global_sp,
+         "blocklets": [{"bh": min(8, bh), "bw": taps, "count": count}]}
+        for (bh, bw, taps, count), keys in groups.items()]}
+    if path is not None:
+        with open(path, "w") as fh:
+            json.dump(cfg, fh, indent=1)
+    return cfg
+
+
+def srmbrep_config(shapes, isp=0.75, path=None):
+    """BASELINE config 4: per-layer "srmbrep" entries shaped like optimal_configs/drn_d_54/*.json (no outer
+    sparsity, RAMANUJAN inner pattern of 1x1 elements on the collapsed (Cout, Cin*kh*kw) matrix, repeated over
+    the outer block): obh = min(128, Cout), obw = 32 (16 when Cin*kh*kw is not a multiple of 32), core block
+    min(32, obh) x obw.  Every (cout tile, K-block) stays live: this is the finer-than-tile sparsity the
+    reference's absent TBT kernel targets; the block-tile kernels run it as a dense layer, bit-exact in the mask."""
+    groups = collections.OrderedDict()
+    for key in prunable_keys(shapes):
+        o, i, kh, kw = shapes[key]
+        cols = i * kh * kw
+        obw = 32 if cols % 32 == 0 else 16
+        obh = min(128, o)
+        groups.setdefault((obh, obw, min(32, obh)), []).append(key)
+    cfg = {"pruner_type": "srmbrep", "configs": [
+        {"layer_set": keys, "obh": obh, "obw": obw, "cbh": cbh, "cbw": obw, "ibh": 1, "ibw": 1, "osp": 0.0,
+         "opat": "RAMANUJAN", "isp": isp, "ipat": "RAMANUJAN", "is_repetitive": True, "collapse_tensor": True,
+         "cross_prob": 0.5, "is_symmetric": False}
+        for (obh, obw, cbh), keys in groups.items()]}
+    if path is not None:
+        with open(path, "w") as fh:
+            json.dump(cfg, fh, indent=1)
+    return cfg
+
+
 def pack_mask_bits(mask):
     """compact storage of a {0, !=0} mask for fixtures"""
     return np.packbits((np.asarray(mask) != 0).reshape(-1))
