@@ -337,6 +337,15 @@ def main():
         dom = [l for l in layers if l["kernel"] == dom_name]
         dom_ms = sum(l["ms"] for l in dom)
         dom_tflops = 2.0 * sum(l["live_gmac"] for l in dom) * 1e9 / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
+        # DRAM traffic per launch from the committed `ncu --set full` capture of the same workload
+        # (tools/ncu_summarize.py traffic -> profiles/ncu_traffic.json); null when there is none for this workload
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = {k: v for k, v in json.load(fh).items() if v.get("workload") == workload(args, B)["workload"]}
+        dom_traffic = traffic.get("conv_tc_row", {}).get("bytes_per_launch") if "ROW" in dom_name else None
+        dom_io = sum(l["hbm_gbs"] * l["ms"] * 1e6 for l in dom) / max(len(dom), 1)    # algorithmic bytes per launch
         if args.layers_out:
             with open(args.layers_out, "w") as fh:
                 json.dump({"per_layer_ms": per_layer, "layers": layers, "batch": B}, fh, indent=1)
@@ -357,7 +366,9 @@ def main():
                          "kernel": "%s (%d launches per step: %s)" % (
                              dom_name, len(dom), ", ".join(l["layer"].replace("layer.", "") for l in dom)),
                          "achieved": dom_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": dom_tflops / pk["tflops"], "traffic": None,
+                         "frac": dom_tflops / pk["tflops"], "traffic": dom_traffic,
+                         "traffic_note": "avg DRAM bytes read+written per launch (ncu --set full, profiles/ncu_traffic.json)"
+                                         "; algorithmic input+output bytes per launch (residual reads excluded): %.0f" % dom_io,
                          "peak_source": pk["src"] + " bf16_tflops_sustained",
                          "flops": "2 x unpruned (mask != 0) MACs of these launches",
                          "ms_per_step": dom_ms},
@@ -366,7 +377,8 @@ def main():
                                    "frac": conv_tflops / pk["tflops"], "ms_per_step": conv_ms},
             "roofline_head": {"bound": "hbm", "kernel": "head (seg GEMM + upsample/argmax)",
                               "achieved": head_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                              "frac": head_gbs / pk["hbm_gbs"], "traffic": None,
+                              "frac": head_gbs / pk["hbm_gbs"],
+                              "traffic": traffic.get("head_fused", {}).get("bytes_per_launch"),
                               "bytes_per_launch": head_bytes, "ms": per_layer["head"]},
             "stem_ms_per_step": per_layer["stem"],
             "macs_per_frame": {"dense_g": dense / B / 1e9, "unpruned_g": live / B / 1e9,

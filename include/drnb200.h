@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRNB200_VERSION 103
+#define DRNB200_VERSION 104
 
 /* error codes */
 #define DRNB200_OK          0
@@ -198,6 +198,22 @@ int drnb200_confusion(const uint8_t* pred, const void* label, int label_is_i64, 
 int drnb200_colorize(const uint8_t* labels, int64_t n_px, const uint8_t* palette, int n_colors,
                      const uint8_t* frames_or_null, float alpha, uint8_t* out_rgb, void* stream);
 int drnb200_labels_to_i64(const uint8_t* labels, int64_t n, int64_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-scale test.  Replaces resize_4d_tensor (semantic_seg.py:471-504: every float32 plane through
+ * PIL `Image.resize((w, h), Image.BILINEAR)` on CPU threads) and the sum over scales of test_ms
+ * (semantic_seg.py:540: `final = sum([resize_4d_tensor(out, w, h) for out in outputs])`):
+ *   acc[N,C,H,W] = (first ? 0 : acc) + resize(src[N,C,Hs,Ws])          float32 NCHW, device pointers
+ * The resampling is Pillow's (src/libImaging/Resample.c): horizontal pass into float32, then vertical pass, each
+ * output sample `ss = 0.0; ss += pixel * k[t]` in double over its taps in order.  The caller passes Pillow's
+ * precompute_coeffs() tables per axis: xmin[W] (first tap), xcnt[W] (taps used), xk[W*kx] (double weights, row
+ * stride kx); kx == 0 means "no horizontal pass" and requires Ws == W (same for y).  Bit-identical to the reference. */
+int drnb200_ms_accumulate(const float* src, int N, int C, int Hs, int Ws, float* acc, int H, int W,
+                          const int32_t* xmin, const int32_t* xcnt, const double* xk, int kx,
+                          const int32_t* ymin, const int32_t* ycnt, const double* yk, int ky,
+                          int first, void* stream);
+/* `pred = final.argmax(axis=1)` (semantic_seg.py:543; first maximum wins): acc float32 [N,C,H,W] -> uint8 [N,H,W] */
+int drnb200_ms_argmax(const float* acc, int N, int C, int H, int W, uint8_t* labels, void* stream);
 
 #ifdef __cplusplus
 }

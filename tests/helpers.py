@@ -37,3 +37,12 @@ def fixture_state_dict(arch, fx):
 def fixture_frames(fx):
     h, w = (int(v) for v in fx["hw"])
     return recipe.make_frames(1, h, w, seed=1234 + int(fx["seed"]))
+
+
+MS_SOURCES = [(32, 56), (16, 28), (24, 42), (40, 70), (48, 84), (56, 98), (23, 37), (77, 131)]
+
+
+def ms_sources(seed=11, n=1, c=4):
+    """the source tensors tests/golden/gen_golden_ms.py fed to the reference's resize_4d_tensor"""
+    g = torch.Generator().manual_seed(seed)
+    return [torch.log_softmax(3.0 * torch.randn(n, c, h, w, generator=g), dim=1) for h, w in MS_SOURCES]

@@ -597,3 +597,100 @@ def test_full_size_uint8_ingest():
     assert torch.equal(a, b)
     col = drnb200.overlay(a, torch.from_numpy(frames).to(dev()))
     assert np.array_equal(col.cpu().numpy(), frameio_oracle.overlay(a.cpu().numpy(), frames))
+
+
+# ------------------------------------------------------------------------------------------------ 8f-4 multi-scale
+def test_multiscale_matches_reference_fixture_bit_exact():
+    """drnb200_ms_accumulate / drnb200_ms_argmax against what the REAL reference produced (resize_4d_tensor through
+    PIL + sum + argmax, tests/golden/gen_golden_ms.py): float32 bit-exact, labels identical"""
+    from helpers import ms_sources
+    from drnb200 import multiscale
+    fx = np.load(golden("multiscale.npz"))
+    H, W = (int(v) for v in fx["target"])
+    srcs = [t.to(dev()) for t in ms_sources()]
+    for i, src in enumerate(srcs):
+        acc = torch.full((src.shape[0], src.shape[1], H, W), float("nan"), device=dev())
+        multiscale.resize_accumulate(src, acc, first=True)
+        assert np.array_equal(acc.cpu().numpy(), fx["dst%d" % i]), tuple(src.shape)
+    final, pred = multiscale.combine(srcs, H, W)
+    assert np.array_equal(final.cpu().numpy(), fx["final"])
+    assert np.array_equal(pred.cpu().numpy().astype(np.int64), fx["pred"])
+
+
+@pytest.mark.parametrize("target", [(64, 136), (33, 57)])
+def test_multiscale_against_oracle(target):
+    """19 classes, two frames, the reference's five scales plus the frame itself; ragged target (scalar argmax path)"""
+    from oracle import ms_oracle
+    from drnb200 import multiscale
+    H, W = target
+    g = torch.Generator().manual_seed(H)
+    srcs = [torch.log_softmax(2.0 * torch.randn(2, 19, int(H * s), int(W * s), generator=g), dim=1)
+            for s in [1.0] + multiscale.SCALES]
+    ref_final, ref_pred = ms_oracle.ms_combine([t.numpy() for t in srcs], W, H)
+    final, pred = multiscale.combine([t.to(dev()) for t in srcs], H, W)
+    assert np.array_equal(final.cpu().numpy(), ref_final)
+    assert np.array_equal(pred.cpu().numpy().astype(np.int64), ref_pred)
+    # first maximum wins on ties (numpy argmax)
+    tie = torch.zeros(1, 19, 8, 12, device=dev())
+    tie[:, 7] = 1.0
+    tie[:, 11] = 1.0
+    assert int(multiscale.argmax_labels(tie).unique().item()) == 7
+    with pytest.raises(ffi.Drnb200Error):
+        multiscale.resize_accumulate(srcs[1], torch.zeros(2, 19, H, W), first=True)      # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("src_hw", [(330, 57), (990, 40), (33, 570), (5, 7)])
+def test_multiscale_large_factors(src_hw):
+    """strong down/up-scaling: generic tap loops and the shorter row strips (scratch sized by the scale factor)"""
+    from oracle import ms_oracle
+    from drnb200 import multiscale
+    H, W = 33, 57
+    src = torch.randn(1, 3, src_hw[0], src_hw[1], generator=torch.Generator().manual_seed(src_hw[0]))
+    ref = ms_oracle.resize_4d_tensor(src.numpy(), W, H)
+    acc = torch.empty(1, 3, H, W, device=dev())
+    multiscale.resize_accumulate(src.to(dev()), acc, first=True)
+    assert np.array_equal(acc.cpu().numpy(), ref)
+    multiscale.resize_accumulate(src.to(dev()), acc, first=False)
+    assert np.array_equal(acc.cpu().numpy(), ref + ref)
+    with pytest.raises(ffi.Drnb200Error):            # factor 100: beyond the scratch, rejected (never silently wrong)
+        multiscale.resize_accumulate(torch.zeros(1, 1, 3300, 8, device=dev()), torch.zeros(1, 1, H, 8, device=dev()), True)
+
+
+def test_multiscale_end_to_end_predict_ms_and_test_ms():
+    """predict_ms / test_ms (mirror of semantic_seg.py:507-557) against the oracle's model + Pillow restatement"""
+    import torch.nn.functional as F
+    from oracle import ms_oracle
+    from drnb200 import multiscale
+    model, sd, x = _gate_case("drn_d_22", 64, 128, 2, True, "fp16", seed=31)
+    images = [x] + [F.interpolate(x, size=(int(64 * s), int(128 * s)), mode="bicubic", align_corners=False)
+                    for s in multiscale.SCALES]
+    ref_out = [drn_oracle.drnseg_forward(sd, im)[0].numpy() for im in images]
+    ref_final, ref_pred = ms_oracle.ms_combine(ref_out, 128, 64)
+    pred = multiscale.predict_ms(model, [im.to(dev()) for im in images])
+    agree = float((pred.cpu().numpy() == ref_pred).mean())
+    print("multi-scale argmax agreement %.5f" % agree)
+    assert agree >= 0.995
+    gt = torch.from_numpy(ref_pred).clone()
+    gt[:, ::5] = 255
+    loader = [(images[0], gt, ["a.png", "b.png"]) + tuple(images[1:])]
+    miou = multiscale.test_ms(loader, model, 19, multiscale.SCALES, has_gt=True)
+    hist = drn_oracle.fast_hist(pred.cpu().numpy().flatten().astype(np.int64), gt.numpy().flatten(), 19)
+    assert miou == drn_oracle.miou(hist)
+    assert abs(miou - drn_oracle.miou(drn_oracle.fast_hist(ref_pred.flatten(), gt.numpy().flatten(), 19))) <= 0.5
+
+
+def test_multiscale_full_size_properties():
+    """size-independent properties at 1024x2048: a single same-size 'scale' reproduces predict(); constant planes
+    survive the 1.75x -> 1x resample exactly (every coefficient row sums to 1)"""
+    from drnb200 import multiscale
+    model, sd, x = _gate_case("drn_d_22", 1024, 2048, 1, True, "fp16", seed=32)
+    xd = x.to(dev())
+    assert torch.equal(multiscale.predict_ms(model, [xd]), model.predict(xd))
+    vals = torch.linspace(-7.0, -0.1, 19, device=dev()).view(1, 19, 1, 1)
+    src = vals.expand(1, 19, 1792, 3584).contiguous()
+    acc = torch.empty(1, 19, 1024, 2048, device=dev())
+    multiscale.resize_accumulate(src, acc, first=True)
+    assert torch.equal(acc, vals.expand_as(acc))
+    multiscale.resize_accumulate(src[:, :, :512, :1024].contiguous(), acc, first=False)
+    assert torch.equal(acc, (vals + vals).expand_as(acc))
+    assert int(multiscale.argmax_labels(acc).unique().item()) == 18

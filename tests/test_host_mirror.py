@@ -229,7 +229,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), name
     lib = ffi.lib()
-    assert lib.drnb200_version() == 103
+    assert lib.drnb200_version() == 104
     # argument validation happens before any CUDA call, so it is testable here
     assert lib.drnb200_compact_mask(None, 8, 8, 3, 3, 8, 8, None, None, None, None) == -1
     assert b"null pointer" in lib.drnb200_last_error()
@@ -302,3 +302,22 @@ def test_checkpoint_ingestion_prefixes_and_prune_buffers(tmp_path):
     # mismatching checkpoints fail loudly
     with pytest.raises(KeyError):
         drnb200.load_checkpoint(dst2, {"layer.nope.weight": torch.zeros(1)})
+
+
+def test_multiscale_coefficient_tables_equal_pillows():
+    """drnb200.multiscale.bilinear_coeffs (vectorised, product) == oracle/ms_oracle.bilinear_coeffs (scalar
+    restatement of Pillow's precompute_coeffs, pinned to the real reference in test_oracle_pinned.py), bit for bit"""
+    from drnb200 import multiscale
+    from oracle import ms_oracle
+    for a, b in [(28, 56), (98, 56), (37, 56), (131, 56), (512, 1024), (1792, 1024), (3584, 2048), (7, 50), (300, 3)]:
+        got, ref = multiscale.bilinear_coeffs(a, b), ms_oracle.bilinear_coeffs(a, b)
+        assert all(np.array_equal(g, r) and g.dtype == r.dtype for g, r in zip(got, ref)), (a, b)
+    assert multiscale.SCALES == [0.5, 0.75, 1.25, 1.5, 1.75]          # semantic_seg.py:578
+
+
+def test_multiscale_fails_loudly_on_cpu_tensors():
+    from drnb200 import multiscale
+    with pytest.raises(ffi.Drnb200Error):
+        multiscale.resize_accumulate(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 8, 8), first=True)
+    with pytest.raises(ffi.Drnb200Error):
+        multiscale.argmax_labels(torch.zeros(1, 2, 8, 8))

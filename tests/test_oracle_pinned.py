@@ -124,3 +124,23 @@ def test_palette_matches_reference():
     assert np.array_equal(frameio_oracle.colorize(fx["pred"]), fx["color"])
     # out-of-palette labels (ignore = 255) take the last row, the rule seg_video.py spells out in a comment
     assert np.array_equal(frameio_oracle.colorize(np.array([255, 19, 18])), fx["palette"][[19, 19, 18]])
+
+
+def test_multiscale_resize_sum_argmax_match_reference():
+    """oracle/ms_oracle.py (Pillow BILINEAR restated) == semantic_seg.resize_4d_tensor / test_ms, bit for bit"""
+    from helpers import MS_SOURCES, ms_sources
+    from oracle import ms_oracle
+    fx = np.load(golden("multiscale.npz"))
+    H, W = (int(v) for v in fx["target"])
+    assert [tuple(s) for s in fx["sources"].tolist()] == MS_SOURCES
+    srcs = [t.numpy() for t in ms_sources()]
+    for i, src in enumerate(srcs):
+        got = ms_oracle.resize_4d_tensor(src, W, H)
+        assert got.dtype == np.float32 and np.array_equal(got, fx["dst%d" % i]), MS_SOURCES[i]
+    final, pred = ms_oracle.ms_combine(srcs, W, H)
+    assert np.array_equal(final, fx["final"]) and np.array_equal(pred, fx["pred"])
+    # the coefficient rows are normalised and the upscaling case is the 2-tap triangle
+    xmin, cnt, kk = ms_oracle.bilinear_coeffs(28, 56)
+    assert kk.shape[1] == 3 and np.allclose(kk.sum(1), 1.0) and cnt.max() <= 3
+    xmin, cnt, kk = ms_oracle.bilinear_coeffs(98, 56)
+    assert kk.shape[1] == 5 and cnt.max() <= 5

@@ -3,9 +3,12 @@
 
   python tools/ncu_summarize.py launches gpurun_out/launches.csv  profiles/r01_ncu_launch_shares.txt
   python tools/ncu_summarize.py full     gpurun_out/conv_tc.ncu-rep profiles/r01_ncu_conv_tc_layers.txt [labels,...]
+  python tools/ncu_summarize.py traffic  gpurun_out/conv_tc.ncu-rep profiles/ncu_traffic.json conv_tc_row "<1, 1, 1" "<workload>"
 
 `launches`: per-kernel totals/shares of a `--metrics gpu__time_duration.sum` launch list (cold-cache, serialised:
-compare shares, not absolutes).  `full`: one row per captured launch of an `ncu --set full` report with the
+compare shares, not absolutes).  `traffic`: average dram__bytes_read.sum + dram__bytes_write.sum per captured launch
+of the kernels whose name contains the filter, stored under a key of profiles/ncu_traffic.json together with the
+workload string of the capture — bench.py copies it into `roofline.traffic` when the workload matches.  `full`: one row per captured launch of an `ncu --set full` report with the
 numbers the roofline keys of bench.py quote (DRAM bytes read+written = `traffic`, tensor-pipe activity, clocks).
 """
 import csv
@@ -79,8 +82,33 @@ def full(src, dst, labels):
     sys.stdout.write(out.getvalue())
 
 
+def traffic(src, dst, key, name_filter, workload):
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    kn, rd, wr, tm = (hdr.index(c) for c in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                                             "gpu__time_duration.sum"))
+    tot, us, n = 0.0, 0.0, 0
+    for r in rows[2:]:
+        if name_filter not in r[kn]:
+            continue
+        tot += (float(r[rd]) * SCALE[units[rd]] + float(r[wr]) * SCALE[units[wr]]) * 1e6
+        us += float(r[tm]) * SCALE[units[tm]]
+        n += 1
+    data = json.load(open(dst)) if os.path.exists(dst) else {}
+    data[key] = {"bytes_per_launch": tot / max(n, 1), "launches_captured": n, "avg_launch_us_under_ncu": us / max(n, 1),
+                 "kernel_filter": name_filter, "workload": workload,
+                 "source": "ncu --set full --clock-control none (%s)" % os.path.basename(src)}
+    json.dump(data, open(dst, "w"), indent=1)
+    print(key, data[key])
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5], sys.argv[6])
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4].split(",") if len(sys.argv) > 4 else [])
