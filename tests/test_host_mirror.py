@@ -321,3 +321,24 @@ def test_multiscale_fails_loudly_on_cpu_tensors():
         multiscale.resize_accumulate(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 8, 8), first=True)
     with pytest.raises(ffi.Drnb200Error):
         multiscale.argmax_labels(torch.zeros(1, 2, 8, 8))
+
+
+def test_rmb_rmcdb_text_export_is_byte_identical(tmp_path):
+    """dump_fpath of prune_tensor_as_rmb / prune_tensor_as_rmcdb (pruners/RmbPruner.py:247-378,
+    pruners/RmcdbPruner.py:320-439) against the files the real reference wrote (gen_golden_export.py)"""
+    import zlib
+    fx = np.load(golden("blocklet_export.npz"))
+    cases = {
+        "rmb_a": (RmbPruner.prune_tensor_as_rmb, W_A, RmbPrunerConfig(32, 72, 0.5, [BlockletType(8, 9)], [2])),
+        "rmb_b": (RmbPruner.prune_tensor_as_rmb, W_B,
+                  RmbPrunerConfig(16, 32, 0.5, [BlockletType(4, 4), BlockletType(2, 8)], [1, 1])),
+        "rmcdb_a": (RmcdbPruner.prune_tensor_as_rmcdb, W_A,
+                    RmcdbPrunerConfig(32, 72, 0.5, [BlockletType(8, 9)], [2], True)),
+        "rmcdb_b": (RmcdbPruner.prune_tensor_as_rmcdb, W_B,
+                    RmcdbPrunerConfig(16, 32, 0.0, [BlockletType(4, 4), BlockletType(2, 8)], [1, 2], True)),
+    }
+    for name, (fn, w, cfg) in cases.items():
+        path = tmp_path / (name + ".txt")
+        mask = _quiet(fn, w, cfg, str(path))
+        _same(name, mask)                                   # exporting does not change the mask
+        assert path.read_bytes() == zlib.decompress(fx[name].tobytes()), name

@@ -15,6 +15,7 @@ import json
 import numpy as np
 
 from .Pruner import Pruner
+from . import blocklet_export
 
 
 class BlockletType(object):
@@ -94,6 +95,7 @@ class RmbPruner(Pruner):
         else:
             keep = np.ones((nrb, ncb), dtype=mat.dtype)
 
+        exported = []          # blocklets in creation order (only kept for the text export)
         for rb in range(nrb):
             for cb in range(ncb):
                 if keep[rb, cb] == 0:
@@ -103,15 +105,19 @@ class RmbPruner(Pruner):
                     n_r, n_c = bh // btype.bh, bw // btype.bw
                     score = np.zeros(n_c)
                     for _ in range(count):
+                        vals, picks = np.zeros((bh, btype.bw)), np.zeros(n_r)
+                        exported.append(blocklet_export.Blocklet(bh, bw, rb, cb, btype.bh, btype.bw, vals, picks))
                         for br in range(n_r):
                             band = blk[br * btype.bh:(br + 1) * btype.bh]
                             for bc in range(n_c):
                                 score[bc] = np.sum(np.abs(band[:, bc * btype.bw:(bc + 1) * btype.bw]))
                             pick = int(np.argmax(score))
+                            vals[br * btype.bh:(br + 1) * btype.bh] = band[:, pick * btype.bw:(pick + 1) * btype.bw]
+                            picks[br] = pick
                             band[:, pick * btype.bw:(pick + 1) * btype.bw] = 0
                             r0 = rb * bh + br * btype.bh
                             c0 = cb * bw + pick * btype.bw
                             mask[r0:r0 + btype.bh, c0:c0 + btype.bw] = 1.0
         if dump_fpath is not None:
-            raise NotImplementedError("RMB text export (pruners/RmbPruner.py:247-378) is not mirrored yet")
+            blocklet_export.write_rmb(dump_fpath, rows, cols, bh, bw, exported)
         return mask.reshape(tensor.shape)

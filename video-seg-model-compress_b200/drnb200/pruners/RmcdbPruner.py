@@ -16,6 +16,7 @@ import json
 import numpy as np
 
 from .Pruner import Pruner
+from . import blocklet_export
 from .RmbPruner import BlockletType, outer_block_mask, parse_blocklet_config
 from .utils import get_meta_matrix
 
@@ -95,6 +96,7 @@ class RmcdbPruner(Pruner):
         keep = np.ones((nrb, ncb), dtype=mat.dtype)
         if config.spo > 0:
             keep = outer_block_mask(mat, bh, bw, config.spo, get_meta_matrix(mat, bh, bw))
+        exported = []          # blocklets in creation order (only kept for the text export)
         for rb in range(nrb):
             for cb in range(ncb):
                 if keep[rb, cb] == 0:
@@ -111,10 +113,16 @@ class RmcdbPruner(Pruner):
                         scores[dia] = np.sum(meta[r_idx, (r_idx % n_c + dia) % n_c])
                     for dia in np.argsort(scores)[::-1][:count]:
                         RmcdbPruner._paint_diagonal(mask, rb, cb, bh, bw, btype, dia)
+                        vals = np.zeros((bh, btype.bw), dtype=mat.dtype)
                         for br in range(n_r):
                             bc = (br + dia) % n_c
+                            vals[br * btype.bh:(br + 1) * btype.bh] = \
+                                blk[br * btype.bh:(br + 1) * btype.bh, bc * btype.bw:(bc + 1) * btype.bw]
                             # literal reproduction of pruners/RmcdbPruner.py:293 (row slice of a row slice)
                             blk[br * btype.bh:(br + 1) * btype.bh][bc * btype.bw:(bc + 1) * btype.bw] = 0
+                            # the reference appends one record PER blocklet row, all sharing the diagonal's values
+                            # (pruners/RmcdbPruner.py:303-304 sits inside the row loop)
+                            exported.append(blocklet_export.Blocklet(bh, bw, rb, cb, btype.bh, btype.bw, vals, dia))
         if dump_fpath is not None:
-            raise NotImplementedError("RMCDB text export (pruners/RmcdbPruner.py:320-439) is not mirrored yet")
+            blocklet_export.write_rmcdb(dump_fpath, rows, cols, bh, bw, exported)
         return mask.reshape(tensor.shape)
