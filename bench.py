@@ -314,7 +314,7 @@ def main():
         KERNELS = {0: "conv_tc<T>", 1: "conv_tc<P>", 2: "conv_tc<T,f32>", 3: "conv_gather", 4: "conv_halo",
                    5: "conv_tc<T,ROW>", -1: "conv_direct"}
         shapes = {-1: (H, W)}
-        for i, op in enumerate(eng.ops):
+        for i, op in enumerate(eng.last_ops or eng.ops):
             src = op.input_from if op.input_from is not None else i - 1
             oh, ow = op.out_hw(*shapes[src])
             shapes[i] = (oh, ow)

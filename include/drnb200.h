@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRNB200_VERSION 104
+#define DRNB200_VERSION 105
 
 /* error codes */
 #define DRNB200_OK          0
@@ -104,7 +104,21 @@ typedef struct drnb200_conv_desc {
   int32_t res_cpitch;       /* channels per pixel of the tensor the residual lives in (>= Cout)              */
   int32_t res_coffset;      /* first channel of the residual inside that tensor                              */
   int32_t relu_n;           /* apply ReLU only to output channels < relu_n (0 = use `relu` for all channels) */
+  /* Residual projection inside the K loop (0 = off).  A BasicBlock whose shortcut is a stride-1 1x1 conv + BN
+   * (drn.py:181-186, layers 5/6 of DRN-D) computes relu(bn2(conv2(h)) + bn_d(proj(x))).  With proj_cin > 0 the
+   * `residual` argument of drnb200_conv_forward is NOT added in the epilogue: it is a second INPUT tensor
+   * [N, H, W, res_cpitch] (act_dtype, same H x W as the output) whose channels [res_coffset, res_coffset + proj_cin)
+   * enter the accumulator through extra K-blocks appended to every output tile's list:
+   *     kblk entry = DRNB200_KB_PROJ + 3 * cib   (cib = 64-channel block of the projection input),
+   * sorted after the conv's own entries, their packed 128x64 weight tiles following in the same order.  The caller
+   * folds the two BatchNorms: proj weights pre-multiplied by scale_d[c]/scale_2[c], bn_shift = shift_2 + shift_d.
+   * Supported by the row-halo tcgen05 kernel only (3x3, stride 1, dilation <= 4, tile 128x64, output rows wider
+   * than 128 pixels); plan creation fails with DRNB200_E_ARG otherwise and the caller keeps the projection as a
+   * separate launch. */
+  int32_t proj_cin;
 } drnb200_conv_desc;
+
+#define DRNB200_KB_PROJ (3 << 20)
 
 typedef struct drnb200_conv_plan drnb200_conv_plan;
 

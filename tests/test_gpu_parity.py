@@ -353,6 +353,39 @@ def test_config5_drn_d_22_unstructured_90():
     assert live < 0.11 * dense and tile > 0.9 * dense        # unstructured zeros leave (almost) every tile live
 
 
+@pytest.mark.parametrize("arch", ["drn_d_22", "drn_d_38"])
+def test_parity_gates_wide_frames_projection_in_k(arch):
+    """frames wider than 1024 pixels switch blocks with a stride-1 1x1 shortcut (layers 5/6) to conv2 with the
+    shortcut inside its K loop (DRNB200_KB_PROJ entries, engine.ProjResidualConv); same gates, 64 x 2048 frame"""
+    from drnb200.engine import ProjResidualConv
+    model, sd, x = _gate_case(arch, 64, 2048, 1, True, "fp16", seed=41)
+    ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
+    ref_lab = torch.max(ref_lp, 1)[1]
+    with torch.no_grad():
+        lp, seg = model(x.to(dev()))
+        lab = model.predict(x.to(dev()))
+    eng = model.engine()
+    assert eng.last_ops is eng.ops_proj and sum(isinstance(o, ProjResidualConv) for o in eng.last_ops) == 2
+    for o in eng.last_ops:
+        if isinstance(o, ProjResidualConv):
+            kb = o.kblk.cpu().numpy()[:o.n_live]
+            assert (kb >= ffi.KB_PROJ).sum() > 0 and ffi.lib().drnb200_conv_plan_mode(list(o.plans.values())[0]) == 5
+    assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL
+    assert rel_err(lp.cpu(), ref_lp) <= LOGIT_RTOL
+    agree = (lab.cpu().long() == ref_lab).float().mean().item()
+    print("argmax agreement (%s, projection in K): %.5f" % (arch, agree))
+    assert agree >= LABEL_AGREE
+    # the two launch lists give the same labels up to the re-rounded projection weights
+    eng.proj_in_k = False
+    lab_b = model.predict(x.to(dev()))
+    assert eng.last_ops is eng.ops
+    assert (lab_b == lab).float().mean().item() >= 0.999
+    dense, live, tile = eng.mac_counts(1, 64, 2048)
+    eng.proj_in_k = True
+    model.predict(x.to(dev()))
+    assert eng.mac_counts(1, 64, 2048) == (dense, live, tile)      # same work counted either way
+
+
 def test_bf16_storage_reported_separately():
     """bf16 activation storage (north_star's nominal layout): logits gate holds; the label agreement is
     reported, and must hold on pixels whose fp32 top-1/top-2 margin exceeds the logit tolerance"""

@@ -229,7 +229,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), name
     lib = ffi.lib()
-    assert lib.drnb200_version() == 104
+    assert lib.drnb200_version() == 105
     # argument validation happens before any CUDA call, so it is testable here
     assert lib.drnb200_compact_mask(None, 8, 8, 3, 3, 8, 8, None, None, None, None) == -1
     assert b"null pointer" in lib.drnb200_last_error()
@@ -342,3 +342,22 @@ def test_rmb_rmcdb_text_export_is_byte_identical(tmp_path):
         mask = _quiet(fn, w, cfg, str(path))
         _same(name, mask)                                   # exporting does not change the mask
         assert path.read_bytes() == zlib.decompress(fx[name].tobytes()), name
+
+
+def test_projection_launch_list_is_chosen_by_frame_width():
+    """engine.ops_proj: blocks with a stride-1 1x1 shortcut as [conv1] + [conv2 + shortcut in K]; same indices and
+    state-dict coverage as the default list; used only when the stage's rows are wider than 128 pixels"""
+    from drnb200.engine import Engine, ProjResidualConv, FusedFirstConv
+    m = drnb200.DRNSeg("drn_d_22", 19, pretrained=False)
+    eng = Engine(m, act_dtype="fp16")
+    assert eng.ops_proj is not None and len(eng.ops_proj) == len(eng.ops)
+    proj = [o for o in eng.ops_proj if isinstance(o, ProjResidualConv)]
+    assert [o.key for o in proj] == ["layer.5.0.conv2", "layer.6.0.conv2"]
+    assert sorted(k for o in eng.ops_proj for k in o.keys) == sorted(k for o in eng.ops for k in o.keys)
+    assert [type(o) for o in eng.ops if isinstance(o, FusedFirstConv)] == [FusedFirstConv] * 4
+    assert eng.ops_for(1024, 2048) is eng.ops_proj and eng.ops_for(64, 1032) is eng.ops_proj
+    assert eng.ops_for(512, 1024) is eng.ops and eng.ops_for(1024, 1024) is eng.ops
+    for i, (a, b) in enumerate(zip(eng.ops, eng.ops_proj)):
+        assert (a is b) or a.key == b.key
+    # a bottleneck network has no such block
+    assert Engine(drnb200.DRNSeg("drn_d_54", 19, pretrained=False), act_dtype="fp16").ops_proj is None

@@ -23,6 +23,7 @@ struct ConvParams {
   int x_cpitch;             // channels per pixel of the tensor x lives in
   int res_pitch, res_coff;  // residual: channels per pixel of its tensor, first channel
   int relu_n;               // ReLU applies to output channels < relu_n (Cout: all, 0: none)
+  int proj;                 // > 0: `residual` is a second input projected by DRNB200_KB_PROJ K-blocks (ROW kernel)
   // ---- tcgen05 path only
   const int32_t* ot_order;  // output tiles sorted by decreasing live count
   int TW, TH, tw_shift;     // pixel tile (powers of two), NT = TW*TH

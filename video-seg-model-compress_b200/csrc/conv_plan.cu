@@ -47,8 +47,17 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
   p.res_pitch = d.res_cpitch > 0 ? d.res_cpitch : d.Cout;
   p.res_coff = d.res_coffset;
   p.relu_n = d.relu_n > 0 ? d.relu_n : (d.relu ? d.Cout : 0);
+  p.proj = d.proj_cin > 0 ? d.proj_cin : 0;
+  if (p.proj && (d.has_residual || d.ksize != 3 || d.stride != 1 || d.proj_cin % 64 || d.tile_o != 128 ||
+                 d.tile_ci != 64 || d.res_cpitch <= 0 || d.impl == DRNB200_IMPL_DIRECT)) {
+    set_error("conv_plan_create: proj_cin=%d needs a 3x3 stride-1 conv with 128x64 tiles, no epilogue residual, "
+              "res_cpitch set and a tcgen05 plan", d.proj_cin);
+    delete plan;
+    return DRNB200_E_ARG;
+  }
+  const int res_width = p.proj ? p.proj : d.Cout;      // channels read from the residual / projection tensor
   if (p.x_cpitch < d.Cin || p.x_cpitch % 8 || p.res_pitch % 8 || p.res_coff % 8 || p.res_coff < 0 ||
-      p.res_coff + d.Cout > p.res_pitch || p.relu_n > d.Cout) {
+      p.res_coff + res_width > p.res_pitch || p.relu_n > d.Cout) {
     set_error("conv_plan_create: bad channel sub-range (x_cpitch=%d res_cpitch=%d res_coffset=%d relu_n=%d)",
               d.x_cpitch, d.res_cpitch, d.res_coffset, d.relu_n);
     delete plan;
@@ -73,8 +82,14 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
     plan->tc_mode = TC_MODE_GATHER;
   } else if (d.impl != DRNB200_IMPL_DIRECT) {
     int rc = conv_tc_setup(plan);
+    if (rc == DRNB200_OK && p.proj && !(plan->tc_mode == 0 && p.row_mode)) {
+      set_error("conv_plan_create: proj_cin needs the row-halo kernel (output rows wider than 128 pixels, "
+                "dilation <= 4); got OW=%d dil=%d", p.OW, p.dil);
+      drnb200_conv_plan_destroy(plan);
+      return DRNB200_E_ARG;
+    }
     if (rc == DRNB200_OK) plan->impl = DRNB200_IMPL_TCGEN05;
-    else if (d.impl == DRNB200_IMPL_TCGEN05 || rc != DRNB200_E_ARG) {
+    else if (d.impl == DRNB200_IMPL_TCGEN05 || rc != DRNB200_E_ARG || p.proj) {
       drnb200_conv_plan_destroy(plan);
       return rc;
     }
@@ -94,12 +109,13 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
 extern "C" int drnb200_conv_forward(drnb200_conv_plan* plan, const void* x_nhwc,
                                     const void* residual_or_null, void* y_nhwc, void* stream) {
   DRN_REQUIRE(plan && x_nhwc && y_nhwc, "conv_forward: null pointer");
-  if (plan->d.has_residual && !residual_or_null) {
-    set_error("conv_forward: plan was built with has_residual but residual is NULL");
+  const bool wants_res = plan->d.has_residual || plan->p.proj;
+  if (wants_res && !residual_or_null) {
+    set_error("conv_forward: plan was built with has_residual / proj_cin but residual is NULL");
     return DRNB200_E_STATE;
   }
   plan->p.x = x_nhwc;
-  plan->p.residual = plan->d.has_residual ? residual_or_null : nullptr;
+  plan->p.residual = wants_res ? residual_or_null : nullptr;
   plan->p.y = y_nhwc;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->impl != DRNB200_IMPL_TCGEN05) return conv_direct_launch(plan, st);

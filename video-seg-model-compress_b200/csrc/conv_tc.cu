@@ -120,7 +120,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     tma_prefetch_desc(&tmap);
     if (MODE == MODE_T) {
       tma_prefetch_desc(&tmap_y);
-      if (p.has_res) tma_prefetch_desc(&tmap_r);
+      if (p.has_res || p.proj) tma_prefetch_desc(&tmap_r);
     }
     for (int b = 0; b < kEpRing; ++b) {
       mbar_init(&sync->rfull[b], 1);
@@ -177,6 +177,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           mbar_wait(&sync->xempty[xs], xph ^ 1u);
           if (p.dbg & 2) {
             if (elect_one()) mbar_arrive(&sync->xfull[xs]);
+          } else if (kb >= DRNB200_KB_PROJ) {
+            // residual projection (1x1, stride 1) as a K-block: 64 channels of the block's INPUT at the 256 output
+            // pixels themselves, no halo; the MMA warp sees a tap with kx = 0 (DRNB200_KB_PROJ is a multiple of 3)
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&sync->xfull[xs], kRowPx * 128);
+              tma_load_4d(&tmap_r, &sync->xfull[xs], sX, p.res_coff + (kb - DRNB200_KB_PROJ) / 3 * 64, c.ox0, c.oy0, c.n);
+            }
           } else if (elect_one()) {
             mbar_arrive_expect_tx(&sync->xfull[xs], kRowBytes);
             const int x0 = c.ox0 - p.dil, y = c.oy0 + (ky - 1) * p.dil;
@@ -732,6 +739,32 @@ static int encode_out_tmap(drnb200_conv_plan* plan, CUtensorMap* map, const void
   return DRNB200_OK;
 }
 
+// residual-projection input [N, H, W, res_pitch]: one row box of 256 pixels x 64 channels, laid out in shared
+// memory exactly like the first 256 pixels of a conv input row (SWIZZLE_128B, zero fill beyond the image)
+static int encode_proj_tmap(drnb200_conv_plan* plan, const void* ptr) {
+  const ConvParams& p = plan->p;
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return DRNB200_E_CUDA;
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)p.res_pitch, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.N};
+  cuuint64_t gstr[3] = {(cuuint64_t)p.res_pitch * 2, (cuuint64_t)p.OW * p.res_pitch * 2,
+                        (cuuint64_t)p.OH * p.OW * p.res_pitch * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)kRowPx, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapDataType dt = plan->d.act_dtype == DRNB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                             : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(&plan->tmap_r, dt, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(projection input) failed with CUresult %d (pitch=%d OW=%d OH=%d N=%d)", (int)r,
+              p.res_pitch, p.OW, p.OH, p.N);
+    return DRNB200_E_CUDA;
+  }
+  return DRNB200_OK;
+}
+
 static int encode_tmap(drnb200_conv_plan* plan, const void* x) {
   const ConvParams& p = plan->p;
   const drnb200_conv_desc& d = plan->d;
@@ -786,12 +819,17 @@ int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st) {
       if (rc) return rc;
       plan->tmap_y_ptr = p.y;
     }
+    if (p.proj && plan->tmap_r_ptr != p.residual) {
+      int rc = encode_proj_tmap(plan, p.residual);
+      if (rc) return rc;
+      plan->tmap_r_ptr = p.residual;
+    }
     if (p.has_res && plan->tmap_r_ptr != p.residual) {
       int rc = encode_out_tmap(plan, &plan->tmap_r, p.residual, p.res_pitch);
       if (rc) return rc;
       plan->tmap_r_ptr = p.residual;
     }
-    if (!p.has_res && plan->tmap_r_ptr == nullptr) plan->tmap_r = plan->tmap_y;   // never dereferenced
+    if (!p.has_res && !p.proj && plan->tmap_r_ptr == nullptr) plan->tmap_r = plan->tmap_y;   // never dereferenced
   } else if (plan->tmap_y_ptr == nullptr) {
     plan->tmap_y = plan->tmap;                                                    // unused by these modes
     plan->tmap_r = plan->tmap;

@@ -9,6 +9,7 @@ Data layout in HBM: activations NHWC 16-bit (bf16 or fp16, ``act_dtype``), one b
 drawn from a size-keyed pool; packed weights = live K-blocks only, in the swizzled shared-memory image.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -198,6 +199,7 @@ class FusedFirstConv(ConvLayer):
 
     def __init__(self, key, block, input_from):
         super().__init__(key + ".conv1", block.conv1, block.bn1, True, input_from=input_from)
+        self.block = block
         self.ds_conv, self.ds_bn = block.downsample[0], block.downsample[1]
         self.ds_key = key + ".downsample.0"
         self.keys = [key + ".conv1", self.ds_key]
@@ -243,6 +245,126 @@ class FusedFirstConv(ConvLayer):
         md3[:, :, 1, 1] = md[:, :, 0, 0]
         return (torch.cat([w1, wd3]).contiguous(), torch.cat([m1, md3]).contiguous(),
                 torch.cat([s1, sd]).contiguous(), torch.cat([b1, bd]).contiguous())
+
+
+class ProjFallback(Exception):
+    """the BatchNorm fold of a residual projection is ill-conditioned: keep the projection as its own output"""
+
+
+class ProjResidualConv(ConvLayer):
+    """conv2 (3x3, stride 1) of a BasicBlock whose shortcut is a STRIDE-1 1x1 conv + BN (drn.py:181-186; layers 5
+    and 6 of DRN-D-22/38), with the shortcut computed INSIDE conv2's K loop instead of being written to HBM by the
+    previous launch and read back as a residual:
+
+        relu(s2*conv2(h) + b2 + sd*proj(x) + bd) = relu(s2*(conv2(h) + proj'(x)) + (b2 + bd)),  proj' = (sd/s2) * proj
+
+    The projection's live 128x64 weight blocks become extra entries (DRNB200_KB_PROJ + 3*cib) at the end of every
+    output tile's K list; the kernel loads their activations from the block's input tensor (passed through the
+    `residual` argument).  proj' is re-rounded to 16 bits after the per-channel rescale (<= 2^-11 relative per
+    weight); when sd/s2 is not finite or exceeds 1024 in magnitude the fold is refused (ProjFallback) and the engine
+    keeps the [conv1 | downsample] form.  Only the row-halo kernel runs this (feature maps wider than 128 pixels)."""
+
+    MAX_RATIO = 1024.0
+
+    def __init__(self, key, block, input_from, proj_from, proj_pitch):
+        super().__init__(key + ".conv2", block.conv2, block.bn2, True, residual_from=proj_from,
+                         input_from=input_from)
+        self.ds_conv, self.ds_bn = block.downsample[0], block.downsample[1]
+        self.ds_key = key + ".downsample.0"
+        self.keys = [key + ".conv2", self.ds_key]
+        self.proj_cin = self.ds_conv.in_channels
+        self.res_cpitch = proj_pitch
+
+    @staticmethod
+    def applicable(block):
+        ds, c1, c2 = block.downsample, block.conv1, block.conv2
+        return (ds is not None and getattr(block, "residual", True) and ds[0].kernel_size == (1, 1)
+                and ds[0].stride == (1, 1) and c1.stride == (1, 1) and c2.kernel_size == (3, 3)
+                and c2.stride == (1, 1) and c2.dilation[0] <= 4 and c2.out_channels % 128 == 0
+                and c2.in_channels % 64 == 0 and ds[0].in_channels % 64 == 0
+                and ds[0].out_channels == c2.out_channels)
+
+    def dense_macs_per_pixel(self):
+        c, d = self.conv, self.ds_conv
+        return c.out_channels * c.in_channels * 9 + d.out_channels * d.in_channels
+
+    def version_key(self, mask_dict):
+        return super().version_key(mask_dict) + _conv_bn_version(self.ds_conv, self.ds_bn, self.ds_key, mask_dict)
+
+    def _compact_and_pack(self, w32, mask32, act_dtype, device):
+        lib, st = ffi.lib(), ffi.stream_ptr()
+        O, I, kh, kw = w32.shape
+        n_ot, n_kb = O // 128, (I // 64) * kh * kw
+        row_ptr = torch.empty(n_ot + 1, dtype=torch.int32, device=device)
+        kblk = torch.empty(max(1, n_ot * n_kb), dtype=torch.int32, device=device)
+        n_live = torch.zeros(1, dtype=torch.int32, device=device)
+        ffi.check(lib.drnb200_compact_mask(ffi.ptr(mask32), O, I, kh, kw, 128, 64, ffi.ptr(row_ptr), ffi.ptr(kblk),
+                                           ffi.ptr(n_live), st), "compact_mask(%s)" % self.key)
+        n = int(n_live.item())
+        packed = torch.empty((max(1, n), 128 * 64), dtype=torch.int16, device=device)
+        ffi.check(lib.drnb200_pack_weights(ffi.ptr(w32), ffi.ptr(mask32), O, I, kh, kw, 128, 64, ffi.ptr(row_ptr),
+                                           ffi.ptr(kblk), act_dtype, ffi.ptr(packed), st), "pack_weights(%s)" % self.key)
+        return row_ptr.cpu().tolist(), kblk[:n], packed[:n], n
+
+    def refresh(self, mask_dict, act_dtype, device):
+        ver = self.version_key(mask_dict) + (act_dtype, str(device))
+        if ver == self.version:
+            return False
+        self.destroy_plans()
+        w2, m2, _ = self._conv_params(self.conv, self.key, mask_dict, device)
+        wd, md, _ = self._conv_params(self.ds_conv, self.ds_key, mask_dict, device)
+        s2, b2, _ = self._bn_affine(self.bn, w2.shape[0], device)
+        sd, bd, _ = self._bn_affine(self.ds_bn, wd.shape[0], device)
+        ratio = sd / s2
+        if not bool(torch.isfinite(ratio).all()) or float(ratio.abs().max()) > self.MAX_RATIO:
+            raise ProjFallback(self.key)
+        self.tile_o, self.tile_ci = 128, 64
+        rp2, kb2, pk2, n2 = self._compact_and_pack(w2, m2, act_dtype, device)
+        rpd, kbd, pkd, nd = self._compact_and_pack((wd * ratio.view(-1, 1, 1, 1)).contiguous(), md, act_dtype, device)
+        # merge per output tile: the conv's own entries, then the projection's (sorted by construction)
+        kbd = kbd * 3 + ffi.KB_PROJ
+        kparts, wparts, row_ptr = [], [], [0]
+        for ot in range(len(rp2) - 1):
+            kparts += [kb2[rp2[ot]:rp2[ot + 1]], kbd[rpd[ot]:rpd[ot + 1]]]
+            wparts += [pk2[rp2[ot]:rp2[ot + 1]], pkd[rpd[ot]:rpd[ot + 1]]]
+            row_ptr.append(row_ptr[-1] + (rp2[ot + 1] - rp2[ot]) + (rpd[ot + 1] - rpd[ot]))
+        self.n_live = n2 + nd
+        self.kblk = torch.cat(kparts + [torch.zeros(1, dtype=torch.int32, device=device)]).contiguous()
+        self.w_packed = torch.cat(wparts + [torch.zeros((1, 128 * 64), dtype=torch.int16, device=device)]).contiguous()
+        self.row_ptr = torch.tensor(row_ptr, dtype=torch.int32, device=device)
+        self.scale, self.shift = s2.contiguous(), (b2 + bd).contiguous()
+        self.live_elems = int(torch.count_nonzero(w2 * m2).item()) + int(torch.count_nonzero(wd * md).item())
+        self.version = ver
+        return True
+
+    def plan(self, N, H, W, act_dtype, impl):
+        k = (N, H, W, act_dtype, impl)
+        p = self.plans.get(k)
+        if p is None:
+            conv = self.conv
+            d = ffi.ConvDesc(N=N, H=H, W=W, Cin=conv.in_channels, Cout=conv.out_channels, ksize=3, stride=1,
+                             dilation=conv.dilation[0], relu=1, has_residual=0, act_dtype=act_dtype, out_f32=0,
+                             tile_o=128, tile_ci=64, impl=ffi.IMPL_TCGEN05, x_cpitch=self.x_cpitch,
+                             res_cpitch=self.res_cpitch, res_coffset=0, relu_n=0, proj_cin=self.proj_cin)
+            h = C.c_void_p()
+            ffi.check(ffi.lib().drnb200_conv_plan_create(
+                C.byref(h), C.byref(d), ffi.ptr(self.row_ptr), ffi.ptr(self.kblk), ffi.ptr(self.w_packed),
+                ffi.ptr(self.scale), ffi.ptr(self.shift)), "conv_plan_create(%s + projection)" % self.key)
+            p = self.plans[k] = h
+        return p
+
+
+def _conv_bn_version(conv, bn, key, mask_dict):
+    if hasattr(conv, "weight_orig") and hasattr(conv, "weight_mask"):
+        ver = (conv.weight_orig._version, conv.weight_mask._version)
+    else:
+        ver = (conv.weight._version,)
+        if mask_dict is not None:
+            for k in (key + ".weight", "module." + key + ".weight"):
+                if k in mask_dict:
+                    ver = ver + (id(mask_dict[k]), mask_dict[k]._version)
+                    break
+    return ver + (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version)
 
 
 def _check_conv(conv, key):
@@ -301,6 +423,8 @@ class Engine:
         self._lut = None
         self.stem_impl = "tcgen05"   # or "direct": CUDA-core fp32 stem (no input rounding), cross-check
         self.launches_per_forward = 0
+        self.proj_in_k = os.environ.get("DRNB200_PROJ", "1") != "0"    # A/B knob: "0" keeps [conv1 | shortcut] everywhere
+        self.last_ops = None
         self._build_graph()
 
     # ---- module tree -> op list ----------------------------------------------------------------
@@ -395,15 +519,40 @@ class Engine:
         if self.stem is None or not ops:
             raise ffi.Drnb200Error("could not find the DRN stem / conv stages")
         self.ops = ops
+        # alternative launch list for wide frames: blocks with a stride-1 1x1 shortcut run as
+        # [conv1] + [conv2 with the shortcut inside its K loop] instead of [conv1 | shortcut] + [conv2 + residual]
+        # (same indices, all other ops shared).  Chosen per frame size by ops_for().
+        self.ops_proj = None
+        alt = list(ops)
+        for i, op in enumerate(ops):
+            if isinstance(op, FusedFirstConv) and ProjResidualConv.applicable(op.block):
+                bkey = op.key[:-len(".conv1")]
+                src = op.input_from
+                pitch = self.stem[0].out_channels if src < 0 else ops[src].out_channels
+                alt[i] = ConvLayer(bkey + ".conv1", op.block.conv1, op.block.bn1, True, input_from=src)
+                alt[i + 1] = ProjResidualConv(bkey, op.block, input_from=i, proj_from=src, proj_pitch=pitch)
+                self.ops_proj = alt
+
+    def ops_for(self, H, W):
+        """the launch list used for [*, 3, H, W] frames"""
+        if self.ops_proj is None or self.conv_impl == ffi.IMPL_DIRECT or not self.proj_in_k:
+            return self.ops
+        shapes = {-1: (H, W)}
+        for i, op in enumerate(self.ops_proj):
+            src = op.input_from if op.input_from is not None else i - 1
+            shapes[i] = op.out_hw(*shapes[src])
+            if isinstance(op, ProjResidualConv) and shapes[i][1] <= 128:     # row-halo kernel: rows > 128 pixels
+                return self.ops
+        return self.ops_proj
 
     # ---- parameters -> device caches -----------------------------------------------------------
     def set_masks(self, mask_dict):
         """attach a Pruner.mask_dict (pruners/Pruner.py:13); None = derive liveness from zeros"""
         self.mask_dict = mask_dict
 
-    def refresh(self, device):
+    def refresh(self, device, ops=None):
         rebuilt = 0
-        for op in self.ops:
+        for op in (self.ops if ops is None else ops):
             rebuilt += bool(op.refresh(self.mask_dict, self.act_dtype, device))
         conv, bn, _ = self.stem
         stem_w, stem_wver = _effective_weight(conv)
@@ -481,7 +630,8 @@ class Engine:
         stem_macs = N * H * W * sconv.out_channels * 147
         dense += stem_macs; live += stem_macs; tile += stem_macs
         shapes = {-1: (H, W)}
-        for i, op in enumerate(self.ops):
+        ops = self.last_ops if self.last_ops is not None and self.last_ops is self.ops_for(H, W) else self.ops
+        for i, op in enumerate(ops):
             src = op.input_from if op.input_from is not None else i - 1
             ih, iw = shapes[src]
             oh, ow = op.out_hw(ih, iw)
@@ -524,7 +674,14 @@ class Engine:
         x = x.contiguous()
         dev = x.device
         lib = ffi.lib()
-        self.refresh(dev)
+        ops = self.ops_for(H, W)
+        try:
+            self.refresh(dev, ops)
+        except ProjFallback:
+            self.ops_proj = None               # ill-conditioned BatchNorm fold: keep the shortcut as its own output
+            ops = self.ops
+            self.refresh(dev, ops)
+        self.last_ops = ops
         st = ffi.stream_ptr()
         adt = self.act_dtype
         launches = 0
@@ -533,12 +690,12 @@ class Engine:
         shapes = {-1: (H, W)}
         # liveness of buffers for pooling
         last_use = {}
-        for i, op in enumerate(self.ops):
+        for i, op in enumerate(ops):
             src = op.input_from if op.input_from is not None else i - 1
             last_use[src] = i
             if op.residual_from is not None:
                 last_use[op.residual_from] = i
-        last_use[len(self.ops) - 1] = len(self.ops)      # consumed by the head
+        last_use[len(ops) - 1] = len(ops)      # consumed by the head
         pool = {}
 
         def take(nelem):
@@ -569,7 +726,7 @@ class Engine:
                           "stem_plan_forward")
         launches += 1
         outs[-1] = y
-        for i, op in enumerate(self.ops):
+        for i, op in enumerate(ops):
             src = op.input_from if op.input_from is not None else i - 1
             ih, iw = shapes[src]
             oh, ow = op.out_hw(ih, iw)
@@ -584,7 +741,7 @@ class Engine:
             outs[i] = yo
             for j in [k for k, last in last_use.items() if last == i]:
                 give(j)
-        last = len(self.ops) - 1
+        last = len(ops) - 1
         h8, w8 = shapes[last]
         hp = self._head_plan(N, h8, w8)
         classes = self.m.seg.out_channels
@@ -604,7 +761,7 @@ class Engine:
 
     def close(self):
         lib = ffi.lib()
-        for op in self.ops:
+        for op in self.ops + (self.ops_proj or []):
             op.destroy_plans()
         for p in self.head_plans.values():
             lib.drnb200_head_plan_destroy(p)

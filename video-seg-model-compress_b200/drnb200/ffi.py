@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libdrnb200.so")
 
 BF16, F16 = 0, 1
 IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05 = 0, 1, 2
+KB_PROJ = 3 << 20        # DRNB200_KB_PROJ: tile-list entries of the residual projection (include/drnb200.h)
 
 
 class Drnb200Error(RuntimeError):
@@ -22,7 +23,8 @@ class ConvDesc(C.Structure):
     """mirror of drnb200_conv_desc"""
     _fields_ = [(n, C.c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "ksize", "stride", "dilation", "relu", "has_residual",
-        "act_dtype", "out_f32", "tile_o", "tile_ci", "impl", "x_cpitch", "res_cpitch", "res_coffset", "relu_n")]
+        "act_dtype", "out_f32", "tile_o", "tile_ci", "impl", "x_cpitch", "res_cpitch", "res_coffset", "relu_n",
+        "proj_cin")]
 
 
 # name -> (restype, argtypes); every symbol include/drnb200.h declares
