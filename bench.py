@@ -133,6 +133,8 @@ def run_reference(args):
     _, sd, _ = build_model(args)
     from drnb200 import synthetic
     x = synthetic.make_frames(1, args.height, args.width, seed=1234)
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is rank 0 alone and takes the whole host
+    torch.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
     threads = torch.get_num_threads()
     with torch.no_grad():
         for _ in range(max(1, min(args.warmup, 1))):
@@ -176,6 +178,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner must not land on stdout
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -375,7 +378,7 @@ def main():
             "roofline_all_convs": {"bound": "tensor", "kernel": "all %d conv launches of one step (stem/seg excluded)" % len(layers),
                                    "achieved": conv_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
                                    "frac": conv_tflops / pk["tflops"], "ms_per_step": conv_ms},
-            "roofline_head": {"bound": "hbm", "kernel": "head (seg GEMM + upsample/argmax)",
+            "roofline_head": {"bound": "hbm", "kernel": "head_fused_kernel (classifier GEMM + x8 upsample + argmax, one launch)",
                               "achieved": head_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                               "frac": head_gbs / pk["hbm_gbs"],
                               "traffic": traffic.get("head_fused", {}).get("bytes_per_launch"),
@@ -385,7 +388,7 @@ def main():
                                "live_tile_g": tile / B / 1e9},
             "miou_vs_random_labels": miou,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported at N=1 only (rank 0 owns the host cores there)
             from oracle import drn_oracle           # cpu_baseline leg: the oracle port, bounded sample
             xs = synthetic.make_frames(1, H, W, seed=1234)
             with torch.no_grad():
