@@ -26,7 +26,14 @@ for _p in (ROOT, os.path.join(ROOT, "video-seg-model-compress_b200")):
 
 import torch  # noqa: E402
 
-METRIC = "pruned DRN-D-22 frames/s @1024x2048"
+METRIC = "pruned DRN-D-22 frames/s @1024x2048"      # BASELINE.json metric (default arguments)
+
+
+def metric_name(args):
+    """the BASELINE metric for the default workload; other --arch/--height/--width runs are labelled as what they are"""
+    if args.arch == "drn_d_22" and (args.height, args.width) == (1024, 2048):
+        return METRIC
+    return "pruned %s frames/s @%dx%d" % (args.arch.upper().replace("_", "-"), args.height, args.width)
 # per-channel statistics of the reference's video set (info.json of the reference)
 INFO_MEAN = (0.29010095242892997, 0.32808144844279574, 0.28696394422942517)
 INFO_STD = (0.1829540508368939, 0.18656561047509476, 0.18447508988480435)
@@ -146,7 +153,7 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     fps = args.steps / dt
     sample = "1 frame %dx%d per step, fp32, %d steps" % (args.height, args.width, args.steps)
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(args), "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload(args, 1),
@@ -353,7 +360,7 @@ def main():
             with open(args.layers_out, "w") as fh:
                 json.dump({"per_layer_ms": per_layer, "layers": layers, "batch": B}, fh, indent=1)
         line = {
-            "metric": METRIC, "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "metric": metric_name(args), "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.act,
             "data": "synthetic", "config": workload(args, B),
