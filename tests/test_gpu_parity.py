@@ -191,6 +191,91 @@ def test_conv_direct_vs_fp32(case):
     _conv_case(N, H, W, cin, cout, k, s, d, relu, res, ffi.BF16, ffi.IMPL_DIRECT, dens, seed=7)
 
 
+@pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
+@pytest.mark.parametrize("geom", [(1, 5, 300, 128, 256, 64, 64, 0, 2), (2, 3, 257, 64, 128, 128, 192, 64, 4),
+                                  (1, 2, 512, 256, 256, 128, 128, 0, 1)])
+def test_conv_projection_k_blocks_vs_fp32(geom, act):
+    """drnb200_conv_desc.proj_cin through the C ABI: 3x3 conv over h plus 1x1 projection of a second tensor x inside
+    the same K loop (DRNB200_KB_PROJ entries), ragged row tiles, tiles with only-conv / only-projection / no entries,
+    projection input as a channel sub-range; vs torch fp32 on the same 16-bit-representable operands"""
+    N, H, W, cin, cout, pcin, ppitch, poff, dil = geom
+    lib, d, st = ffi.lib(), dev(), ffi.stream_ptr()
+    g = torch.Generator().manual_seed(W + cin)
+    tdt = torch.bfloat16 if act == ffi.BF16 else torch.float16
+    n_ot = cout // 128
+    h = torch.randn(N, cin, H, W, generator=g).to(tdt)
+    xfull = torch.randn(N, ppitch, H, W, generator=g).to(tdt)
+    w = recipe.round_bf16(torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5)
+    wp = recipe.round_bf16(torch.randn(cout, pcin, 1, 1, generator=g) * (2.0 / pcin) ** 0.5)
+    blocks = (torch.rand(n_ot, cin // 64, generator=g) < 0.6).float()
+    pblocks = (torch.rand(n_ot, pcin // 64, generator=g) < 0.7).float()
+    blocks[0] = 0                                  # output tile 0: projection entries only
+    pblocks[0, 0] = 1
+    if n_ot > 1:
+        pblocks[1] = 0                             # output tile 1: conv entries only
+        blocks[1, 0] = 1
+    mask = torch.kron(blocks, torch.ones(128, 64))[:, :, None, None].expand(-1, -1, 3, 3).contiguous()
+    pmask = torch.kron(pblocks, torch.ones(128, 64))[:, :, None, None].contiguous()
+    w, wp = w * mask, wp * pmask
+    scale = 0.5 + torch.rand(cout, generator=g)
+    shift = 0.2 * torch.randn(cout, generator=g)
+    xs = xfull[:, poff:poff + pcin]
+    ref = torch.nn.functional.conv2d(h.float(), w.to(tdt).float(), None, 1, dil, dil) \
+        + torch.nn.functional.conv2d(xs.float(), wp.to(tdt).float())
+    ref = (ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu()
+
+    def compact_pack(wt, mk, k):
+        O, I = wt.shape[:2]
+        wd_, md_ = wt.contiguous().to(d), mk.contiguous().to(d)
+        rp = torch.empty(O // 128 + 1, dtype=torch.int32, device=d)
+        kb = torch.empty(max(1, (O // 128) * (I // 64) * k * k), dtype=torch.int32, device=d)
+        nl = torch.zeros(1, dtype=torch.int32, device=d)
+        ffi.check(lib.drnb200_compact_mask(ffi.ptr(md_), O, I, k, k, 128, 64, ffi.ptr(rp), ffi.ptr(kb), ffi.ptr(nl), st))
+        n = int(nl.item())
+        pk = torch.empty((max(1, n), 128 * 64), dtype=torch.int16, device=d)
+        ffi.check(lib.drnb200_pack_weights(ffi.ptr(wd_), ffi.ptr(md_), O, I, k, k, 128, 64, ffi.ptr(rp), ffi.ptr(kb),
+                                           act, ffi.ptr(pk), st))
+        return rp.cpu().tolist(), kb[:n], pk[:n]
+
+    rp2, kb2, pk2 = compact_pack(w, mask, 3)
+    rpd, kbd, pkd = compact_pack(wp, pmask, 1)
+    kbd = kbd * 3 + ffi.KB_PROJ
+    kparts, wparts, row_ptr = [], [], [0]
+    for ot in range(n_ot):
+        kparts += [kb2[rp2[ot]:rp2[ot + 1]], kbd[rpd[ot]:rpd[ot + 1]]]
+        wparts += [pk2[rp2[ot]:rp2[ot + 1]], pkd[rpd[ot]:rpd[ot + 1]]]
+        row_ptr.append(row_ptr[-1] + rp2[ot + 1] - rp2[ot] + rpd[ot + 1] - rpd[ot])
+    kblk = torch.cat(kparts + [torch.zeros(1, dtype=torch.int32, device=d)]).contiguous()
+    packed = torch.cat(wparts + [torch.zeros((1, 128 * 64), dtype=torch.int16, device=d)]).contiguous()
+    rp = torch.tensor(row_ptr, dtype=torch.int32, device=d)
+    desc = ffi.ConvDesc(N=N, H=H, W=W, Cin=cin, Cout=cout, ksize=3, stride=1, dilation=dil, relu=1, has_residual=0,
+                        act_dtype=act, out_f32=0, tile_o=128, tile_ci=64, impl=ffi.IMPL_TCGEN05, res_cpitch=ppitch,
+                        res_coffset=poff, proj_cin=pcin)
+    plan = C.c_void_p()
+    sc, sh = scale.to(d), shift.to(d)
+    ffi.check(lib.drnb200_conv_plan_create(C.byref(plan), C.byref(desc), ffi.ptr(rp), ffi.ptr(kblk), ffi.ptr(packed),
+                                           ffi.ptr(sc), ffi.ptr(sh)))
+    assert lib.drnb200_conv_plan_mode(plan) == 5                       # row-halo kernel
+    hd = h.permute(0, 2, 3, 1).contiguous().to(d)
+    xd = xfull.permute(0, 2, 3, 1).contiguous().to(d)
+    y = torch.full((N, H, W, cout), float("nan"), dtype=tdt, device=d)
+    with pytest.raises(ffi.Drnb200Error):
+        ffi.check(lib.drnb200_conv_forward(plan, ffi.ptr(hd), None, ffi.ptr(y), st))     # projection input missing
+    ffi.check(lib.drnb200_conv_forward(plan, ffi.ptr(hd), ffi.ptr(xd), ffi.ptr(y), st))
+    torch.cuda.synchronize()
+    lib.drnb200_conv_plan_destroy(plan)
+    got = y.float().permute(0, 3, 1, 2).cpu()
+    assert torch.isfinite(got).all()
+    tol = (2.0 ** -8 if act == ffi.BF16 else 2.0 ** -10) * max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() <= tol
+    # unsupported geometries are refused (the caller keeps the projection as its own launch)
+    bad = ffi.ConvDesc(N=N, H=H, W=64, Cin=cin, Cout=cout, ksize=3, stride=1, dilation=dil, relu=1, has_residual=0,
+                       act_dtype=act, out_f32=0, tile_o=128, tile_ci=64, impl=ffi.IMPL_TCGEN05, res_cpitch=ppitch,
+                       res_coffset=poff, proj_cin=pcin)
+    assert lib.drnb200_conv_plan_create(C.byref(plan), C.byref(bad), ffi.ptr(rp), ffi.ptr(kblk), ffi.ptr(packed),
+                                        ffi.ptr(sc), ffi.ptr(sh)) != 0
+
+
 # ------------------------------------------------------------------------------------------ end to end
 def _build(arch, sd, masks, act):
     m = drnb200.DRNSeg(arch, 19, pretrained_model=None, pretrained=False, act_dtype=act)
