@@ -44,6 +44,22 @@ def main():
     ms = timed(lambda: multiscale.argmax_labels(acc))
     out["argmax"] = {"ms": ms, "gbs": (4 * C + 1) * H * W / ms / 1e6}
     out["combine_ms_per_frame"] = total + ms
+    if "--model" in sys.argv:
+        # whole multi-scale prediction of one frame (semantic_seg.test_ms loop body): six forward() calls of the pruned
+        # DRN-D-22 (log-probs materialised per scale, as the reference does) + resize/sum/argmax, all on the device
+        import types
+        import torch.nn.functional as F
+        sys.path.insert(0, ROOT)
+        import bench
+        args = types.SimpleNamespace(arch="drn_d_22", act="fp16", sparsity=0.75)
+        model, _, _ = bench.build_model(args, dev)
+        x = torch.randn(1, 3, H, W, device=dev)
+        images = [x] + [F.interpolate(x, size=(int(H * s), int(W * s)), mode="bilinear") for s in multiscale.SCALES]
+        single = timed(lambda: model.predict(x), iters=5)
+        full = timed(lambda: multiscale.predict_ms(model, images), iters=5)
+        fwd = timed(lambda: [model(im)[0] for im in images], iters=3)
+        out["predict_ms"] = {"ms_per_frame": full, "six_forward_calls_ms": fwd, "single_scale_predict_ms": single,
+                             "pixels_vs_single_scale": sum(s * s for s in [1.0] + multiscale.SCALES)}
     print(json.dumps(out))
 
 
