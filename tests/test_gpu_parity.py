@@ -748,6 +748,19 @@ def test_multiscale_against_oracle(target):
     final, pred = multiscale.combine([t.to(dev()) for t in srcs], H, W)
     assert np.array_equal(final.cpu().numpy(), ref_final)
     assert np.array_equal(pred.cpu().numpy().astype(np.int64), ref_pred)
+    # guard bands around the accumulator and the label map: the kernels write nothing outside their tensors
+    G = 4096
+    flat = torch.full((2 * 19 * H * W + 2 * G,), -7.0, device=dev())
+    acc = flat[G:G + 2 * 19 * H * W].view(2, 19, H, W)
+    for i, t in enumerate(srcs):
+        multiscale.resize_accumulate(t.to(dev()), acc, first=(i == 0))
+    lflat = torch.full((2 * H * W + 2 * G,), 200, dtype=torch.uint8, device=dev())
+    lab = lflat[G:G + 2 * H * W].view(2, H, W)
+    ffi.check(ffi.lib().drnb200_ms_argmax(ffi.ptr(acc), 2, 19, H, W, ffi.ptr(lab), ffi.stream_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(acc.cpu().numpy(), ref_final) and np.array_equal(lab.cpu().numpy().astype(np.int64), ref_pred)
+    assert bool((flat[:G] == -7.0).all()) and bool((flat[-G:] == -7.0).all())
+    assert bool((lflat[:G] == 200).all()) and bool((lflat[-G:] == 200).all())
     # first maximum wins on ties (numpy argmax)
     tie = torch.zeros(1, 19, 8, 12, device=dev())
     tie[:, 7] = 1.0
