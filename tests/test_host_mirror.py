@@ -361,3 +361,23 @@ def test_projection_launch_list_is_chosen_by_frame_width():
         assert (a is b) or a.key == b.key
     # a bottleneck network has no such block
     assert Engine(drnb200.DRNSeg("drn_d_54", 19, pretrained=False), act_dtype="fp16").ops_proj is None
+
+
+def test_multiscale_coefficient_properties_random_sizes():
+    """properties of Pillow's tables for arbitrary axis sizes: rows normalised, windows inside the source and
+    non-decreasing, tap count bounded by ksize — what the kernel's scratch sizing (rows_for) relies on"""
+    from drnb200 import multiscale
+    rng = np.random.RandomState(5)
+    for _ in range(200):
+        a, b = int(rng.randint(1, 700)), int(rng.randint(1, 700))
+        lo, cnt, kk = multiscale.bilinear_coeffs(a, b)
+        scale = a / b
+        support = max(scale, 1.0)
+        assert kk.shape == (b, int(np.ceil(support)) * 2 + 1)
+        assert (cnt >= 1).all() and (cnt <= kk.shape[1]).all() and (lo >= 0).all() and (lo + cnt <= a).all()
+        assert np.allclose(kk.sum(1), 1.0, atol=1e-12) and (kk >= 0).all()
+        assert (np.diff(lo) >= 0).all() and (np.diff(lo + cnt) >= 0).all()
+        # rows a strip of TY output rows touches: the bound drnb200_ms_accumulate sizes its shared-memory scratch with
+        for ty in (16, 4, 1):
+            need = max(int(lo[min(y0 + ty, b) - 1] + cnt[min(y0 + ty, b) - 1] - lo[y0]) for y0 in range(0, b, ty))
+            assert need <= int((ty - 1) * scale + 2.0 * support) + 2, (a, b, ty, need)
