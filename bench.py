@@ -162,6 +162,36 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """multi-rank runs: bind this process to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host
+    buffers are allocated (first touch puts their pages on that node), so every rank's H2D stream reads local DRAM.
+    Returns a short description for the JSON line; does nothing when the topology is not exposed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                       # nvml pads the PCI domain to 8 hex digits
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return "numa_node not exposed"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "node %d has no CPU in this process's affinity mask" % node
+        os.sched_setaffinity(0, cpus)
+        return "rank bound to NUMA node %d (%d CPUs)" % (node, len(cpus))
+    except Exception as exc:                                  # topology files missing, no NVML, no permission
+        return "not bound (%s)" % type(exc).__name__
+
+
 def workload(args, batch):
     return {"workload": "%s BlockPruner %.0f%% block-sparse, batch %d/GPU, %dx%d, act %s" % (
         args.arch, 100 * args.sparsity, batch, args.height, args.width, args.act),
@@ -185,6 +215,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    numa = pin_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     if world > 1:
         import torch.distributed as dist
         # NCCL printf()s its version banner to stdout while the communicator is created: keep stdout for the JSON line
@@ -381,6 +412,7 @@ def main():
                 "d2h_bytes_per_step": B * H * W,
                 "note": "same pipeline fed with uint8 HWC frames; ToTensor+Normalize fused into the stem kernel"},
             "gpu_launches": launches,
+            "host_numa": numa,
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor",
                          "kernel": "%s (%d launches per step: %s)" % (
