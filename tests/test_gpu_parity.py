@@ -606,6 +606,27 @@ def test_confusion_matrix_and_ignore_label():
     assert np.array_equal(tiny.cpu().numpy(), fx["tiny"])
 
 
+def test_eval_loop_mirrors_of_test_and_val_miou(tmp_path):
+    """evalops.test / evalops.val_miou (semantic_seg.py:429-468, :638-671) on a two-batch loader: mIoU equals the
+    reference formula on the label maps predict() returns; save_vis writes the label and palette PNGs"""
+    from drnb200 import evalops
+    model, sd, x = _gate_case("drn_d_22", 64, 128, 4, True, "fp16", seed=51)
+    gt = torch.randint(0, 19, (4, 64, 128), generator=torch.Generator().manual_seed(52))
+    gt[:, :3] = 255
+    loader = [(x[:2], gt[:2], ["a/f0.png", "a/f1.png"]), (x[2:], gt[2:], ["b/f2.png", "b/f3.png"])]
+    with torch.no_grad():
+        pred = model.predict(x.to(dev())).cpu().numpy().astype(np.int64)
+    want = drn_oracle.miou(drn_oracle.fast_hist(pred.flatten(), gt.numpy().flatten(), 19))
+    out = str(tmp_path / "pred")
+    assert evalops.test(loader, model, 19, output_dir=out, has_gt=True, save_vis=True) == want
+    assert evalops.val_miou([(b[0], b[1]) for b in loader], model, 19) == want
+    assert evalops.test(loader, model, 19, has_gt=False) is None
+    from PIL import Image
+    lab = np.asarray(Image.open(out + "/b/f2.png"))
+    col = np.asarray(Image.open(out + "_color/b/f2.png"))
+    assert np.array_equal(lab, pred[2]) and np.array_equal(col, drnb200.CITYSCAPE_PALETTE[pred[2]])
+
+
 def test_full_size_properties():
     """BASELINE size (1024x2048): size-independent properties instead of a minutes-long CPU oracle run:
     (i) tcgen05 and CUDA-core direct kernels agree layer for layer on the same tile lists,

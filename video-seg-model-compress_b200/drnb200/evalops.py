@@ -72,3 +72,47 @@ class ConfusionMeter:
     def miou(self):
         """``round(np.nanmean(per_class_iu(hist) * 100), 2)``   (semantic_seg.py:466-468)"""
         return round(float(np.nanmean(self.ious())), 2)
+
+
+def _save_vis(pred, names, output_dir, num_classes):
+    """save_output_images / save_colorful_images (semantic_seg.py:84-112): label PNG + palette PNG per frame"""
+    import os
+    from PIL import Image
+    from .frameio import CITYSCAPE_PALETTE, colorize
+    palette = np.asarray([[0, 0, 0], [217, 83, 79], [91, 192, 222]], np.uint8) if num_classes == 3 \
+        else CITYSCAPE_PALETTE                       # TRIPLET_PALETTE (RGB part) / CITYSCAPE_PALETTE, :52-77
+    color = colorize(pred, palette).cpu().numpy()
+    lab = pred.cpu().numpy()
+    for ind in range(len(names)):
+        for arr, root in ((lab[ind], output_dir), (color[ind], output_dir + "_color")):
+            fn = os.path.join(root, names[ind][:-4] + ".png")
+            os.makedirs(os.path.split(fn)[0] or ".", exist_ok=True)
+            Image.fromarray(arr).save(fn)
+
+
+def test(eval_data_loader, model, num_classes, output_dir="pred", has_gt=True, save_vis=False, device=None,
+         all_reduce=True):
+    """signature and return value of semantic_seg.test (semantic_seg.py:429-468): batches `(image, label, name)`,
+    `model(image)[0]` + `torch.max(final, 1)` replaced by `model.predict(image)`, the confusion matrix accumulated
+    on the device and (with several ranks, each iterating its own shard of the loader) summed over NCCL before the
+    mIoU `round(nanmean(per_class_iu(hist)) * 100, 2)` is taken.  Returns None without ground truth."""
+    model.eval()
+    device = device if device is not None else next(model.parameters()).device
+    meter = ConfusionMeter(num_classes, device)
+    for batch in eval_data_loader:
+        image, label, name = batch[0], (batch[1] if has_gt else None), batch[-1]
+        pred = model.predict(image.to(device, non_blocking=True))
+        if save_vis:
+            _save_vis(pred, name, output_dir, num_classes)
+        if has_gt:
+            meter.update(pred, label.to(device, non_blocking=True))
+    if has_gt:
+        if all_reduce:
+            meter.all_reduce()
+        return meter.miou()
+
+
+def val_miou(val_loader, model, num_classes, args=None, has_gt=True, device=None, all_reduce=True):
+    """semantic_seg.val_miou (semantic_seg.py:638-671): as test() for loaders yielding `(image, label)`"""
+    return test(((im, lb, None) for im, lb in val_loader), model, num_classes, has_gt=has_gt, save_vis=False,
+                device=device, all_reduce=all_reduce)
