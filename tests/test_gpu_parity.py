@@ -471,6 +471,26 @@ def test_parity_gates_wide_frames_projection_in_k(arch):
     assert eng.mac_counts(1, 64, 2048) == (dense, live, tile)      # same work counted either way
 
 
+@pytest.mark.parametrize("hw", [(300, 300), (100, 156), (77, 204)])
+def test_frame_sizes_that_are_not_multiples_of_8(hw):
+    """seg_video_old.py:127 resizes frames to 300x300: the stride-2 stages round up (150, 75, 38) and `up` returns
+    8*38 = 304 rows, exactly like the reference; logits and labels against the oracle at such sizes"""
+    model, sd, x = _gate_case("drn_d_22", hw[0], hw[1], 1, True, "fp16", seed=61)
+    ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
+    ref_lab = torch.max(ref_lp, 1)[1]
+    with torch.no_grad():
+        lp, seg = model(x.to(dev()))
+        lab = model.predict(x.to(dev()))
+    h8, w8 = -(-hw[0] // 8), -(-hw[1] // 8)
+    assert tuple(ref_seg.shape[2:]) == (h8, w8) and tuple(seg.shape) == tuple(ref_seg.shape)
+    assert tuple(lab.shape) == (1, 8 * h8, 8 * w8) == tuple(ref_lab.shape) and lp.shape == ref_lp.shape
+    assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL and rel_err(lp.cpu(), ref_lp) <= LOGIT_RTOL
+    agree = (lab.cpu().long() == ref_lab).float().mean().item()
+    print("argmax agreement at %dx%d: %.5f" % (hw[0], hw[1], agree))
+    assert agree >= 0.998
+    assert torch.equal(torch.max(lp, 1)[1].to(torch.uint8), lab)
+
+
 def test_bf16_storage_reported_separately():
     """bf16 activation storage (north_star's nominal layout): logits gate holds; the label agreement is
     reported, and must hold on pixels whose fp32 top-1/top-2 margin exceeds the logit tolerance"""
@@ -542,7 +562,7 @@ def test_apply_masks_invalidates_the_cache():
 def test_input_validation():
     model, sd, x = _gate_case("drn_d_22", 64, 128, 1, False, "fp16", seed=11)
     with pytest.raises(ffi.Drnb200Error):
-        model.predict(torch.zeros(1, 3, 60, 64, device=dev()))       # H % 8 != 0
+        model.predict(torch.zeros(1, 3, 60, 62, device=dev()))       # W % 4 != 0
     with pytest.raises(ffi.Drnb200Error):
         model.predict(torch.zeros(1, 3, 64, 64, device=dev(), dtype=torch.float16))
     out = model.predict(torch.zeros(3, 3, 72, 200, device=dev()))    # ragged map sizes (9 x 25 at 1/8)

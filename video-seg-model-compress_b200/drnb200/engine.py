@@ -669,8 +669,11 @@ class Engine:
                 raise ffi.Drnb200Error("input must be a float32 CUDA tensor [N,3,H,W] (got %s %s on %s); "
                                        "there is no CPU path" % (tuple(x.shape), x.dtype, x.device))
             N, _, H, W = x.shape
-        if H % 8 or W % 8:
-            raise ffi.Drnb200Error("H and W must be multiples of 8 (got %dx%d)" % (H, W))
+        # any H; W % 4 == 0 (the float32 frame rows must be 16-byte multiples for TMA).  Like the reference the
+        # stride-2 stages round up, so the label map is 8*ceil(H/8) x 8*ceil(W/8) (300x300 -> 304x304,
+        # seg_video_old.py:127)
+        if W % 4 or H < 8 or W < 8:
+            raise ffi.Drnb200Error("W must be a multiple of 4 and H, W >= 8 (got %dx%d)" % (H, W))
         x = x.contiguous()
         dev = x.device
         lib = ffi.lib()
