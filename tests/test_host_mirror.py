@@ -381,3 +381,25 @@ def test_multiscale_coefficient_properties_random_sizes():
         for ty in (16, 4, 1):
             need = max(int(lo[min(y0 + ty, b) - 1] + cnt[min(y0 + ty, b) - 1] - lo[y0]) for y0 in range(0, b, ty))
             assert need <= int((ty - 1) * scale + 2.0 * support) + 2, (a, b, ty, need)
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """ABI drift guard: every prototype in include/drnb200.h has as many parameters as its ctypes signature, and
+    the ConvDesc mirror has exactly the fields of drnb200_conv_desc, in order"""
+    header = open(os.path.join(ROOT, "include", "drnb200.h")).read()
+    code = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    for name, (_, argtypes) in ffi.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\(([^)]*)\)\s*;" % name, code)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(argtypes), (name, n, len(argtypes))
+    body = re.search(r"typedef struct drnb200_conv_desc \{(.*?)\} drnb200_conv_desc;", code, flags=re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            assert decl.startswith("int32_t"), decl
+            fields += [f.strip() for f in decl[len("int32_t"):].split(",")]
+    assert fields == [f for f, _ in ffi.ConvDesc._fields_]
+    assert int(re.search(r"#define DRNB200_KB_PROJ \((\d+) << (\d+)\)", header).group(1)) << 20 == ffi.KB_PROJ
