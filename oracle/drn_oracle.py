@@ -30,8 +30,13 @@ def _bn(x, sd, key):
     return x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
 
 
-def backbone_forward(sd, x, prefix="layer", taps=None, raw=None):
+def backbone_forward(sd, x, prefix="layer", taps=None, raw=None, quant=None):
     """Run the DRN backbone (everything in DRNSeg.layer) on float32 NCHW `x`.
+
+    `quant`, if a callable ``quant(role, key, tensor) -> tensor``, is applied wherever the CUDA path STORES a
+    tensor in 16 bits (role "input": the frame; "act": a conv+bn(+res)+relu output; "shortcut": a downsample
+    output) — a storage-precision emulation for the error-budget analysis (tests/precision_budget.py); None
+    (the default) leaves this the plain fp32 restatement.
 
     `taps`, if a dict, receives every conv+bn(+res)(+relu) output keyed by the conv's state_dict prefix
     (NCHW float32) — used by the per-layer parity tests.  `raw`, if a dict, receives the bare nn.Conv2d
@@ -42,6 +47,10 @@ def backbone_forward(sd, x, prefix="layer", taps=None, raw=None):
             raw[key] = out
         return out
 
+    def store(role, key, t):
+        return t if quant is None else quant(role, key, t)
+
+    x = store("input", "frame", x)
     keys = [k for k in sd.keys() if k.startswith(prefix + ".")]
     top = sorted({int(k.split(".")[1]) for k in keys})
     arch_d = (prefix + ".0.0.weight") in sd           # arch D: child 0 is Sequential(conv7, bn, relu)
@@ -49,13 +58,13 @@ def backbone_forward(sd, x, prefix="layer", taps=None, raw=None):
     # arch D children: layer0..layer8 -> indices 0..8 ; arch C: conv1, bn1, relu, layer1..layer8 -> 0,1,(2),3..10
     if arch_d:
         x = conv2d(prefix + ".0.0", x, stride=1, padding=3)      # drn.py:132-137
-        x = F.relu(_bn(x, sd, prefix + ".0.1"))
+        x = store("act", prefix + ".0.0", F.relu(_bn(x, sd, prefix + ".0.1")))
         if taps is not None:
             taps[prefix + ".0.0"] = x
         stage_of = {i: i for i in top if i >= 1}
     else:
         x = conv2d(prefix + ".0", x, stride=1, padding=3)        # drn.py:123-127
-        x = F.relu(_bn(x, sd, prefix + ".1"))
+        x = store("act", prefix + ".0", F.relu(_bn(x, sd, prefix + ".1")))
         if taps is not None:
             taps[prefix + ".0"] = x
         stage_of = {i: i - 2 for i in top if i >= 3}
@@ -73,7 +82,7 @@ def backbone_forward(sd, x, prefix="layer", taps=None, raw=None):
             for n, ci in enumerate(convs):
                 ck = base + ".%d" % ci
                 x = conv2d(ck, x, stride=stride if n == 0 else 1, padding=dil, dilation=dil)
-                x = F.relu(_bn(x, sd, base + ".%d" % (ci + 1)))
+                x = store("act", ck, F.relu(_bn(x, sd, base + ".%d" % (ci + 1))))
                 if taps is not None:
                     taps[ck] = x
             continue
@@ -88,29 +97,30 @@ def backbone_forward(sd, x, prefix="layer", taps=None, raw=None):
             bottleneck = (bk + ".conv3.weight") in sd
             resid = x
             if bottleneck:                                                          # drn.py:86-106
-                out = F.relu(_bn(conv2d(bk + ".conv1", x), sd, bk + ".bn1"))
+                out = store("act", bk + ".conv1", F.relu(_bn(conv2d(bk + ".conv1", x), sd, bk + ".bn1")))
                 if taps is not None:
                     taps[bk + ".conv1"] = out
-                out = F.relu(_bn(conv2d(bk + ".conv2", out, stride=bstride, padding=d2, dilation=d2),
-                                 sd, bk + ".bn2"))
+                out = store("act", bk + ".conv2", F.relu(_bn(
+                    conv2d(bk + ".conv2", out, stride=bstride, padding=d2, dilation=d2), sd, bk + ".bn2")))
                 if taps is not None:
                     taps[bk + ".conv2"] = out
                 out = _bn(conv2d(bk + ".conv3", out), sd, bk + ".bn3")
                 last = bk + ".conv3"
             else:                                                                   # drn.py:49-65
-                out = F.relu(_bn(conv2d(bk + ".conv1", x, stride=bstride, padding=d1, dilation=d1),
-                                 sd, bk + ".bn1"))
+                out = store("act", bk + ".conv1", F.relu(_bn(
+                    conv2d(bk + ".conv1", x, stride=bstride, padding=d1, dilation=d1), sd, bk + ".bn1")))
                 if taps is not None:
                     taps[bk + ".conv1"] = out
                 out = _bn(conv2d(bk + ".conv2", out, padding=d2, dilation=d2), sd, bk + ".bn2")
                 last = bk + ".conv2"
             if (bk + ".downsample.0.weight") in sd:                                 # drn.py:181-186
-                resid = _bn(conv2d(bk + ".downsample.0", x, stride=bstride), sd, bk + ".downsample.1")
+                resid = store("shortcut", bk + ".downsample.0",
+                              _bn(conv2d(bk + ".downsample.0", x, stride=bstride), sd, bk + ".downsample.1"))
                 if taps is not None:
                     taps[bk + ".downsample.0"] = resid
             if not no_residual:
                 out = out + resid
-            x = F.relu(out)
+            x = store("act", last, F.relu(out))
             if taps is not None:
                 taps[last] = x
     return x
@@ -137,12 +147,12 @@ def head_forward(sd, feat, up_weight=None):
 
 
 @torch.no_grad()
-def drnseg_forward(sd, x, prefix=None, taps=None, raw=None):
+def drnseg_forward(sd, x, prefix=None, taps=None, raw=None, quant=None):
     """DRNSeg.forward(x) -> (logprob [N,C,H,W], seg_logits [N,C,H/8,W/8])  fp32 on CPU"""
     sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items() if torch.is_floating_point(v)}
     if prefix is None:
         prefix = "layer" if any(k.startswith("layer.") for k in sd) else "base"
-    feat = backbone_forward(sd, x.detach().to("cpu", torch.float32), prefix, taps, raw)
+    feat = backbone_forward(sd, x.detach().to("cpu", torch.float32), prefix, taps, raw, quant)
     return head_forward(sd, feat)
 
 

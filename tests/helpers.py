@@ -46,3 +46,33 @@ def ms_sources(seed=11, n=1, c=4):
     """the source tensors tests/golden/gen_golden_ms.py fed to the reference's resize_4d_tensor"""
     g = torch.Generator().manual_seed(seed)
     return [torch.log_softmax(3.0 * torch.randn(n, c, h, w, generator=g), dim=1) for h, w in MS_SOURCES]
+
+
+def gate_case_cpu(arch, pruned, seed, cfg=None):
+    """(model on the CPU, state_dict, mask_dict) of a seeded random-init network, pruned by the host mirror of the
+    reference's pruners when `pruned` (cfg = a pruner JSON dict, default BlockPruner 75 %)"""
+    import contextlib
+    import io
+    import tempfile
+    import drnb200
+    shapes = load_keys(arch)
+    sd = recipe.make_state_dict(shapes, seed=seed)
+    model = drnb200.DRNSeg(arch, 19, pretrained=False)
+    model.load_state_dict(sd, strict=False)
+    masks = None
+    if pruned:
+        cfg = cfg if cfg is not None else recipe.block_pruner_config(shapes, 0.75)
+        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
+            json.dump(cfg, fh)
+        pruner = drnb200.pruners.make_pruner(fh.name, on_gpu=False)
+        np.random.seed(seed)                       # srmbrep patterns draw from numpy's global RNG
+        with contextlib.redirect_stdout(io.StringIO()):      # RmbPruner prints progress like the reference
+            if cfg["pruner_type"] == "rmb":
+                pruner.generate_masks(model)       # RmbPruner.generate_masks has no is_static (RmbPruner.py:111)
+            else:
+                pruner.generate_masks(model, is_static=False)
+        os.unlink(fh.name)
+        masks = pruner.mask_dict
+        sd = recipe.sparse_reinit(sd, masks, seed=seed)
+        model.load_state_dict(sd, strict=False)
+    return model, sd, masks

@@ -5,6 +5,8 @@ logits within 2e-2 relative; mIoU within 0.1 point.  Run on the GPU box: pytest 
 """
 import collections
 import ctypes as C
+import json
+import os
 
 import numpy as np
 import pytest
@@ -12,13 +14,26 @@ import torch
 
 import drnb200
 from drnb200 import ffi
-from helpers import fixture_frames, fixture_state_dict, golden, load_keys
+from conftest import ROOT
+from helpers import fixture_frames, fixture_state_dict, gate_case_cpu, golden, load_keys
 from oracle import compact_oracle, drn_oracle, recipe
 
 pytestmark = pytest.mark.gpu
 
 LOGIT_RTOL = 2e-2        # north_star: "logits within 2e-2 relative" (relative to the logit range)
-LABEL_AGREE = 0.999      # north_star: ">= 99.9 % of pixels"
+LABEL_AGREE = 0.999      # north_star: ">= 99.9 % of pixels" — asserted on ALL pixels for fp16 storage (the default)
+MIOU_TOL = 0.1           # north_star: "mIoU within 0.1 point"
+
+PARITY_LOG = os.path.join(ROOT, "gpurun_out", "parity_table.jsonl")
+
+
+def record(case, **values):
+    """append one measured parity row (pytest -q hides prints): gpurun_out/parity_table.jsonl on the GPU box, summarised
+    into the tracked profiles/r02_parity_table.txt by tools/parity_table.py"""
+    os.makedirs(os.path.dirname(PARITY_LOG), exist_ok=True)
+    with open(PARITY_LOG, "a") as fh:
+        fh.write(json.dumps(dict(case=case, **{k: (float(v) if isinstance(v, (float, np.floating)) else v)
+                                              for k, v in values.items()})) + "\n")
 
 
 def dev():
@@ -302,7 +317,9 @@ E2E = [("fwd_drn_d_22_64x128_dense.npz", "drn_d_22"), ("fwd_drn_d_22_64x128_bloc
 @pytest.mark.parametrize("name,arch", E2E)
 @pytest.mark.parametrize("act", ["fp16", "bf16"])
 def test_forward_against_golden_fixture(name, arch, act):
-    """small frames: CUDA path vs the outputs the real reference produced (tests/golden)"""
+    """small frames: CUDA path vs the outputs the REAL reference produced (tests/golden).  These maps hold 2048-8192
+    pixels, so ONE flipped pixel is 0.012-0.05 %: the label gate is asserted as "at most max(2, 0.1 %) pixels differ"
+    for fp16; bf16 storage is the reported exception (profiles/r02_precision_budget.txt)."""
     fx = np.load(golden(name))
     sd, masks = fixture_state_dict(arch, fx)
     model = _build(arch, sd, masks, act)
@@ -313,88 +330,127 @@ def test_forward_against_golden_fixture(name, arch, act):
     torch.cuda.synchronize()
     ref_seg = torch.from_numpy(fx["seg"])
     assert seg.shape == ref_seg.shape and logprob.shape[2:] == x.shape[2:]
-    tol = LOGIT_RTOL if act == "fp16" else 2 * LOGIT_RTOL     # tiny maps + random nets: bf16 is looser
-    assert rel_err(seg.cpu(), ref_seg) <= tol
     # forward()[0] and predict() agree with each other exactly
     assert torch.equal(torch.max(logprob, 1)[1].to(torch.uint8), labels)
-    agree = (labels.cpu().numpy() == fx["labels"]).mean()
-    assert agree >= (0.99 if act == "fp16" else 0.97), agree
+    differ = int((labels.cpu().numpy() != fx["labels"]).sum())
+    npx = fx["labels"].size
+    e_seg = rel_err(seg.cpu(), ref_seg)
     sample = logprob[0, :, ::7, ::13].cpu().numpy()
-    assert np.abs(sample - fx["logprob_sample"]).max() <= tol * np.abs(fx["seg"]).max() * 1.5
+    e_lp = float(np.abs(sample - fx["logprob_sample"]).max() / np.abs(fx["seg"]).max())
+    record("real-reference fixture %s" % name.replace(".npz", ""), act=act, frames="1x%dx%d" % tuple(x.shape[2:]),
+           label_agreement=1.0 - differ / npx, pixels_differ=differ, pixels=npx, logits_rel_err=e_seg,
+           logprob_rel_err=e_lp)
+    assert e_seg <= LOGIT_RTOL and e_lp <= LOGIT_RTOL
+    if act == "fp16":
+        assert differ <= max(2, int(npx * (1 - LABEL_AGREE))), (differ, npx)
+    else:
+        assert differ <= int(0.03 * npx), (differ, npx)
+
+
+def test_real_video_frames_against_the_real_reference():
+    """SURVEY 8(d) inputs: three frames of the reference's sample.mp4, decoded / resized / normalised by the reference's
+    own FrameCapture transforms (tests/golden/gen_golden_frames.py), block-pruned DRN-D-22; labels and low-res logits
+    the REAL reference produced are in the fixture.  Both ingest routes: float32 NCHW and the fused uint8 path."""
+    from oracle import frameio_oracle
+    fx = np.load(golden("real_frames.npz"))
+    model, sd, _ = _gate_case("drn_d_22", 64, 128, 1, True, "fp16", seed=int(fx["seed"]))
+    x = frameio_oracle.ingest(fx["frames_u8"], fx["mean"], fx["std"])
+    assert np.array_equal(x[0].numpy(), fx["x0"])                       # the reference's own transform, bit for bit
+    ref_lab = torch.from_numpy(fx["labels"].astype(np.int64))
+    assert float((ref_lab[0] != ref_lab[1]).float().mean()) > 0.01      # the network looks at the frames
+    lab, oracle_lab = _gates("real frames sample.mp4 D-22 BlockPruner 75% 256x448", model, sd, x)
+    assert torch.equal(oracle_lab, ref_lab)                             # oracle == real reference on these frames
+    agree = (lab == ref_lab).float().mean().item()
+    with torch.no_grad():
+        seg = model(x.to(dev()))[1]
+        model.set_ingest(fx["mean"], fx["std"])
+        lab_u8 = model.predict(torch.from_numpy(fx["frames_u8"]).to(dev()))
+    assert rel_err(seg.cpu(), torch.from_numpy(fx["seg"])) <= LOGIT_RTOL
+    assert torch.equal(lab_u8.cpu().long(), lab)                        # fused uint8 ingest: identical labels
+    assert agree >= LABEL_AGREE
+    # bf16 storage on the same frames: reported
+    model.set_act_dtype("bf16")
+    model.set_masks(model._mask_dict)
+    with torch.no_grad():
+        lab_b = model.predict(x.to(dev())).cpu().long()
+    record("real frames sample.mp4 D-22 BlockPruner 75% 256x448", act="bf16", frames="3x256x448",
+           label_agreement=(lab_b == ref_lab).float().mean().item())
 
 
 def _gate_case(arch, h, w, n, pruned, act, seed, cfg=None):
-    shapes = load_keys(arch)
-    sd = recipe.make_state_dict(shapes, seed=seed)
-    model = drnb200.DRNSeg(arch, 19, pretrained=False, act_dtype=act)
-    model.load_state_dict(sd, strict=False)
-    masks = None
-    if pruned:
-        import contextlib, io, json, tempfile, os
-        cfg = cfg if cfg is not None else recipe.block_pruner_config(shapes, 0.75)
-        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
-            json.dump(cfg, fh)
-        pruner = drnb200.pruners.make_pruner(fh.name, on_gpu=False)
-        np.random.seed(seed)                       # srmbrep patterns draw from numpy's global RNG
-        with contextlib.redirect_stdout(io.StringIO()):      # RmbPruner prints progress like the reference
-            if cfg["pruner_type"] == "rmb":
-                pruner.generate_masks(model)       # RmbPruner.generate_masks has no is_static (RmbPruner.py:111)
-            else:
-                pruner.generate_masks(model, is_static=False)
-        os.unlink(fh.name)
-        masks = pruner.mask_dict
-        sd = recipe.sparse_reinit(sd, masks, seed=seed)
-        model.load_state_dict(sd, strict=False)
+    model, sd, masks = gate_case_cpu(arch, pruned, seed, cfg)
+    model.set_act_dtype(act)
     model = model.to(dev()).eval()
     model.set_masks(masks)
     x = recipe.make_frames(n, h, w, seed=99 + seed)
     return model, sd, x
 
 
+def _gates(tag, model, sd, x, act="fp16", min_agree=LABEL_AGREE, logit_tol=LOGIT_RTOL, ref=None, frames_differ=True):
+    """the four north-star gates of one case against the fp32 oracle, on ALL pixels: low-res logits and log-probs
+    within `logit_tol` of the logit range, argmax agreement >= min_agree, predict() == argmax(forward()[0]) bit for
+    bit, mIoU of both label maps against a synthetic ground truth within 0.1 point.  Returns (labels, ref labels)."""
+    ref_lp, ref_seg = ref if ref is not None else drn_oracle.drnseg_forward(sd, x)
+    ref_lab = torch.max(ref_lp, 1)[1]
+    xd = x.to(dev())
+    with torch.no_grad():
+        lp, seg = model(xd)
+        lab = model.predict(xd)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.max(lp, 1)[1].to(torch.uint8), lab)
+    e_seg, e_lp = rel_err(seg.cpu(), ref_seg), rel_err(lp.cpu(), ref_lp)
+    labc = lab.cpu().long()
+    agree = (labc == ref_lab).float().mean().item()
+    top2 = ref_lp.topk(2, dim=1)[0]
+    confident = (top2[:, 0] - top2[:, 1]) > LOGIT_RTOL * ref_seg.abs().max()
+    agree_conf = (labc == ref_lab)[confident].float().mean().item()
+    gt = torch.randint(0, 19, ref_lab.shape, generator=torch.Generator().manual_seed(3))
+    gt[ref_lab % 5 == 0] = 255
+    gt = torch.where(torch.rand(gt.shape, generator=torch.Generator().manual_seed(4)) < 0.5, ref_lab, gt)
+    ref_hist = drn_oracle.fast_hist(ref_lab.numpy().flatten(), gt.numpy().flatten(), 19)
+    meter = drnb200.ConfusionMeter(19, dev())
+    meter.update(lab, gt.to(dev()))
+    assert np.array_equal(meter.hist.cpu().numpy(),
+                          drn_oracle.fast_hist(labc.numpy().flatten(), gt.numpy().flatten(), 19))
+    d_miou = abs(meter.miou() - drn_oracle.miou(ref_hist))
+    # the synthetic network must actually look at its input, otherwise label parity says nothing about the front
+    # kernels (round 1's 2x2-block recipe usually produced networks whose output ignored the frame)
+    differ = float((ref_lab[0] != ref_lab[-1]).float().mean()) if x.shape[0] > 1 else None
+    record(tag, act=act, frames="%dx%dx%d" % (x.shape[0], x.shape[2], x.shape[3]), label_agreement=agree,
+           label_agreement_confident=agree_conf, confident_fraction=confident.float().mean().item(),
+           logits_rel_err=e_seg, logprob_rel_err=e_lp, miou_delta=d_miou, classes=len(ref_lab.unique()),
+           ref_labels_differ_between_frames=differ, asserted_min_agreement=min_agree)
+    assert e_seg <= logit_tol and e_lp <= logit_tol, (tag, e_seg, e_lp)
+    assert agree >= min_agree, (tag, agree)
+    assert agree_conf >= LABEL_AGREE, (tag, agree_conf)
+    assert d_miou <= MIOU_TOL, (tag, d_miou)
+    if frames_differ and differ is not None:
+        assert differ > 0.01, (tag, "the synthetic network ignores its input", differ)
+    return labc, ref_lab
+
+
 @pytest.mark.parametrize("pruned", [False, True])
 def test_parity_gates_drn_d_22(pruned):
     """the north-star gates at 256x512 (oracle finishes in seconds): fp16 activation storage"""
     model, sd, x = _gate_case("drn_d_22", 256, 512, 2, pruned, "fp16", seed=5)
-    ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
-    ref_lab = torch.max(ref_lp, 1)[1]
-    with torch.no_grad():
-        lp, seg = model(x.to(dev()))
-        lab = model.predict(x.to(dev()))
-    assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL
-    assert rel_err(lp.cpu(), ref_lp) <= LOGIT_RTOL
-    agree = (lab.cpu().long() == ref_lab).float().mean().item()
-    print("argmax agreement (fp16, pruned=%s): %.5f" % (pruned, agree))
-    assert agree >= LABEL_AGREE
-    # mIoU of both label maps against a synthetic ground truth: within 0.1 point
-    gt = torch.randint(0, 19, ref_lab.shape, generator=torch.Generator().manual_seed(3))
-    gt[ref_lab % 5 == 0] = 255
-    gt = torch.where(torch.rand(gt.shape, generator=torch.Generator().manual_seed(4)) < 0.5, ref_lab, gt)
-    ref_miou = drn_oracle.miou(drn_oracle.fast_hist(ref_lab.numpy().flatten(), gt.numpy().flatten(), 19))
-    meter = drnb200.ConfusionMeter(19, dev())
-    meter.update(lab, gt.to(dev()))
-    assert np.array_equal(meter.hist.cpu().numpy(),
-                          drn_oracle.fast_hist(lab.cpu().numpy().flatten().astype(np.int64), gt.numpy().flatten(), 19))
-    assert abs(meter.miou() - ref_miou) <= 0.1
+    _gates("config 2 D-22 %s 256x512" % ("BlockPruner 75%" if pruned else "dense"), model, sd, x)
+
+
+def test_parity_gates_at_benchmark_size():
+    """BASELINE config 2 at ITS OWN size: two 1024x2048 frames of block-pruned DRN-D-22 through the launch list the
+    benchmark times (13 ROW launches, projection in K, fused head) against the fp32 oracle on the same frames — all
+    four gates on all pixels.  The oracle takes ~1 s per frame on the GPU box's host cores."""
+    model, sd, x = _gate_case("drn_d_22", 1024, 2048, 2, True, "fp16", seed=12)
+    lab, ref_lab = _gates("config 2 D-22 BlockPruner 75% 1024x2048 (benchmark size)", model, sd, x)
+    eng = model.engine()
+    modes = [ffi.lib().drnb200_conv_plan_mode(p) for op in eng.last_ops for p in op.plans.values()]
+    assert eng.last_ops is eng.ops_proj and modes.count(5) == 13        # the launch list bench.py measures
+    # uint8 labels straight from the fused head equal the int64 labels of torch.max on the host, frame by frame
+    assert lab.shape == (2, 1024, 2048)
 
 
 def _check_config_case(model, sd, x, min_agree, tag):
-    """logits gate + label agreement (all pixels, and pixels whose fp32 margin exceeds the logit tolerance)"""
-    ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
-    ref_lab = torch.max(ref_lp, 1)[1]
-    with torch.no_grad():
-        lp, seg = model(x.to(dev()))
-        lab = model.predict(x.to(dev())).cpu().long()
-    assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL
-    assert torch.equal(torch.max(lp, 1)[1].cpu(), lab)
-    top2 = ref_lp.topk(2, dim=1)[0]
-    confident = (top2[:, 0] - top2[:, 1]) > LOGIT_RTOL * ref_seg.abs().max()
-    agree_all = (lab == ref_lab).float().mean().item()
-    agree_conf = (lab == ref_lab)[confident].float().mean().item()
-    print("%s: logits rel err %.2e, argmax agreement %.5f (confident %.1f %% of pixels: %.5f), %d classes" % (
-        tag, rel_err(seg.cpu(), ref_seg), agree_all, 100 * confident.float().mean().item(), agree_conf,
-        len(ref_lab.unique())))
-    assert agree_conf >= LABEL_AGREE and agree_all >= min_agree
-    return lab, ref_lab
+    return _gates(tag, model, sd, x, min_agree=min_agree, frames_differ=False)
 
 
 def test_config3_drn_d_38_rmb_masks():
@@ -402,7 +458,7 @@ def test_config3_drn_d_38_rmb_masks():
     shapes = load_keys("drn_d_38")
     model, sd, x = _gate_case("drn_d_38", 128, 256, 2, True, "fp16", seed=21,
                               cfg=recipe.rmb_pruner_config(shapes, 0.5))
-    _check_config_case(model, sd, x, 0.995, "config 3 (D-38, rmb)")
+    _check_config_case(model, sd, x, LABEL_AGREE, "config 3 D-38 RmbPruner 128x256")
     dense, live, tile = model.engine().mac_counts(1, 128, 256)
     assert live < 0.2 * dense and tile < 0.62 * dense        # dead outer blocks are skipped as tiles
 
@@ -413,7 +469,7 @@ def test_config4_drn_d_54_srmbrep_masks():
     shapes = load_keys("drn_d_54")
     model, sd, x = _gate_case("drn_d_54", 128, 256, 1, True, "fp16", seed=22,
                               cfg=recipe.srmbrep_config(shapes, 0.75))
-    _check_config_case(model, sd, x, 0.995, "config 4 (D-54, srmbrep)")
+    _check_config_case(model, sd, x, LABEL_AGREE, "config 4 D-54 srmbrep 128x256")
     dense, live, tile = model.engine().mac_counts(1, 128, 256)
     assert live < 0.3 * dense and tile > 0.95 * dense
 
@@ -433,7 +489,7 @@ def test_config5_drn_d_22_unstructured_90():
             nz = float((eff[k] != 0).float().mean())
             assert abs(nz - 0.1) < 0.01, (k, nz)
             sd[k] = eff[k].detach().cpu().clone()
-    _check_config_case(model, sd, x, 0.99, "config 5 (D-22, unstructured 90 %)")
+    _check_config_case(model, sd, x, LABEL_AGREE, "config 5 D-22 unstructured 90% 128x256")
     dense, live, tile = model.engine().mac_counts(1, 128, 256)
     assert live < 0.11 * dense and tile > 0.9 * dense        # unstructured zeros leave (almost) every tile live
 
@@ -444,22 +500,14 @@ def test_parity_gates_wide_frames_projection_in_k(arch):
     shortcut inside its K loop (DRNB200_KB_PROJ entries, engine.ProjResidualConv); same gates, 64 x 2048 frame"""
     from drnb200.engine import ProjResidualConv
     model, sd, x = _gate_case(arch, 64, 2048, 1, True, "fp16", seed=41)
-    ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
-    ref_lab = torch.max(ref_lp, 1)[1]
-    with torch.no_grad():
-        lp, seg = model(x.to(dev()))
-        lab = model.predict(x.to(dev()))
+    lab, ref_lab = _gates("wide frames %s BlockPruner 75%% 64x2048 (projection in K)" % arch, model, sd, x)
+    lab = lab.to(torch.uint8).to(dev())
     eng = model.engine()
     assert eng.last_ops is eng.ops_proj and sum(isinstance(o, ProjResidualConv) for o in eng.last_ops) == 2
     for o in eng.last_ops:
         if isinstance(o, ProjResidualConv):
             kb = o.kblk.cpu().numpy()[:o.n_live]
             assert (kb >= ffi.KB_PROJ).sum() > 0 and ffi.lib().drnb200_conv_plan_mode(list(o.plans.values())[0]) == 5
-    assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL
-    assert rel_err(lp.cpu(), ref_lp) <= LOGIT_RTOL
-    agree = (lab.cpu().long() == ref_lab).float().mean().item()
-    print("argmax agreement (%s, projection in K): %.5f" % (arch, agree))
-    assert agree >= LABEL_AGREE
     # the two launch lists give the same labels up to the re-rounded projection weights
     eng.proj_in_k = False
     lab_b = model.predict(x.to(dev()))
@@ -477,53 +525,70 @@ def test_frame_sizes_that_are_not_multiples_of_8(hw):
     8*38 = 304 rows, exactly like the reference; logits and labels against the oracle at such sizes"""
     model, sd, x = _gate_case("drn_d_22", hw[0], hw[1], 1, True, "fp16", seed=61)
     ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
-    ref_lab = torch.max(ref_lp, 1)[1]
-    with torch.no_grad():
-        lp, seg = model(x.to(dev()))
-        lab = model.predict(x.to(dev()))
     h8, w8 = -(-hw[0] // 8), -(-hw[1] // 8)
-    assert tuple(ref_seg.shape[2:]) == (h8, w8) and tuple(seg.shape) == tuple(ref_seg.shape)
-    assert tuple(lab.shape) == (1, 8 * h8, 8 * w8) == tuple(ref_lab.shape) and lp.shape == ref_lp.shape
-    assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL and rel_err(lp.cpu(), ref_lp) <= LOGIT_RTOL
-    agree = (lab.cpu().long() == ref_lab).float().mean().item()
-    print("argmax agreement at %dx%d: %.5f" % (hw[0], hw[1], agree))
-    assert agree >= 0.998
-    assert torch.equal(torch.max(lp, 1)[1].to(torch.uint8), lab)
+    assert tuple(ref_seg.shape[2:]) == (h8, w8) and tuple(ref_lp.shape[2:]) == (8 * h8, 8 * w8)
+    lab, ref_lab = _gates("odd frame size D-22 BlockPruner 75%% %dx%d" % hw, model, sd, x, ref=(ref_lp, ref_seg))
+    assert tuple(lab.shape) == (1, 8 * h8, 8 * w8) == tuple(ref_lab.shape)
 
 
-def test_bf16_storage_reported_separately():
-    """bf16 activation storage (north_star's nominal layout): logits gate holds; the label agreement is
-    reported, and must hold on pixels whose fp32 top-1/top-2 margin exceeds the logit tolerance"""
-    model, sd, x = _gate_case("drn_d_22", 256, 512, 1, True, "bf16", seed=6)
-    ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
-    ref_lab = torch.max(ref_lp, 1)[1]
+def test_bf16_storage_is_the_measured_exception():
+    """bf16 activation storage (north_star's nominal layout).  Logits, log-probs and mIoU gates hold; the 99.9 % label
+    gate does NOT on random-init networks and cannot with bf16 conv operands: replaying the engine's roundings inside
+    the fp32 oracle gives 99.5-99.6 % for bf16 everywhere and still only 99.85 % with an fp32 residual stream and an
+    fp32 hand-off into the head (profiles/r02_precision_budget.txt).  Asserted here: the measured floor (>= 99.3 %
+    of all pixels), 99.9 % on pixels whose fp32 top-1/top-2 margin exceeds the logit tolerance, and that the
+    disagreement is what the emulation predicts (bf16 rounding, not a kernel defect): <= 2x the emulated count."""
+    model, sd, x = _gate_case("drn_d_22", 256, 512, 2, True, "bf16", seed=5)
+    ref = drn_oracle.drnseg_forward(sd, x)
+    lab, ref_lab = _gates("config 2 D-22 BlockPruner 75% 256x512", model, sd, x, act="bf16", min_agree=0.993, ref=ref)
+    emu_lp, _ = drn_oracle.drnseg_forward(sd, x, quant=lambda role, key, t: t.to(torch.bfloat16).float())
+    emu_dis = (emu_lp.argmax(1) != ref_lab).float().mean().item()
+    dis = (lab != ref_lab).float().mean().item()
+    record("config 2 D-22 BlockPruner 75% 256x512: CPU emulation of bf16 storage", act="bf16(emulated)",
+           frames="2x256x512", label_agreement=1.0 - emu_dis)
+    assert dis <= 2.0 * emu_dis + 1e-4, (dis, emu_dis)
+
+
+@pytest.mark.parametrize("act", ["fp16", "bf16"])
+@pytest.mark.parametrize("case", [("drn_d_22", 64, 128, True), ("drn_d_22", 64, 2048, True), ("drn_d_54", 64, 128, False)])
+def test_per_layer_outputs_track_the_oracle(case, act):
+    """EVERY stored activation of the engine (stem, each conv+BN(+res)+ReLU output, each stored shortcut) against
+    the oracle tap of the same layer, NHWC 16-bit -> NCHW fp32.  Bound per layer: max |diff| <= (depth+4) * ulp(range),
+    i.e. half-ulp storage rounding of this layer plus the propagated roundings of the `depth` layers before it;
+    the table goes to the parity log."""
+    arch, h, w, pruned = case
+    model, sd, x = _gate_case(arch, h, w, 1, pruned, act, seed=8)
+    ref = {}
+    drn_oracle.drnseg_forward(sd, x, taps=ref)
+    got = {}
     with torch.no_grad():
-        seg = model(x.to(dev()))[1]
-        lab = model.predict(x.to(dev())).cpu().long()
-    assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL
-    top2 = ref_lp.topk(2, dim=1)[0]
-    margin = top2[:, 0] - top2[:, 1]
-    confident = margin > LOGIT_RTOL * ref_seg.abs().max()
-    agree_all = (lab == ref_lab).float().mean().item()
-    agree_conf = (lab == ref_lab)[confident].float().mean().item()
-    print("argmax agreement bf16: all %.5f, confident pixels (%.1f %%) %.5f" % (
-        agree_all, 100 * confident.float().mean().item(), agree_conf))
-    assert agree_conf >= LABEL_AGREE and agree_all >= 0.98
-
-
-def test_per_layer_outputs_track_the_oracle():
-    """every fused conv+BN(+res)+ReLU output vs the oracle tap of the same layer (error relative to range)"""
-    model, sd, x = _gate_case("drn_d_22", 64, 128, 1, True, "fp16", seed=8)
-    taps = {}
-    drn_oracle.drnseg_forward(sd, x, taps=taps)
+        model.engine().run(x.to(dev()), want_labels=True, taps=got)
+    torch.cuda.synchronize()
     eng = model.engine()
-    # run the engine layer by layer through its public ops (same launches as run())
-    with torch.no_grad():
-        model.predict(x.to(dev()))
-    assert eng.launches_per_forward == 1 + len(eng.ops) + 1      # stem + convs + ONE fused head launch
-    dense, live, tile = eng.mac_counts(1, 64, 128)
-    assert live < dense and live <= tile <= dense
-    assert abs(live / dense - 0.27) < 0.03          # 75 % of the 24 prunable layers + dense stem/seg
+    assert eng.launches_per_forward == 1 + len(eng.last_ops) + 1      # stem + convs + ONE fused head launch
+    ulp = 2.0 ** -8 if act == "bf16" else 2.0 ** -11
+    rows, depth = [], 0
+    # shortcuts folded into conv2's K loop (projection in K) are never stored: every OTHER oracle tap must be present
+    folded = {k for op in eng.last_ops for k in op.keys[1:] if not isinstance(op, drnb200.engine.FusedFirstConv)}
+    assert set(ref) - folded == set(got), (sorted(set(ref) - folded - set(got)), sorted(set(got) - set(ref)))
+    for key in ref:
+        if key not in got:
+            continue
+        depth += 1
+        a, b = got[key].cpu(), ref[key]
+        assert a.shape == b.shape, (key, a.shape, b.shape)
+        rng = float(b.abs().max())
+        err = float((a - b).abs().max())
+        rms = float((a - b).pow(2).mean().sqrt())
+        rows.append((key, err / rng, rms / rng))
+        assert err <= (depth + 4) * ulp * rng, (key, err, rng, depth)
+    record("per-layer max/rms error relative to the layer's range: %s %dx%d %s" % (
+        arch, h, w, "BlockPruner 75%" if pruned else "dense"), act=act,
+        layers=[{"layer": k, "max": round(e, 6), "rms": round(r, 7)} for k, e, r in rows])
+    dense, live, tile = eng.mac_counts(1, h, w)
+    assert live <= tile <= dense
+    if pruned:
+        assert abs(live / dense - 0.27) < 0.03          # 75 % of the 24 prunable layers + dense stem/seg
 
 
 def test_masks_from_zeros_and_from_torch_prune_give_the_same_tiles():
@@ -557,6 +622,54 @@ def test_apply_masks_invalidates_the_cache():
     b = model.predict(xd)
     op = [o for o in model.engine().ops if o.key == "layer.8.0"][0]
     assert op.n_live == 0 and not torch.equal(a, b)
+
+
+def test_data_writes_need_invalidate_or_verify_weights():
+    """`p.data` writes bypass the autograd version counter the cache is keyed on: stale until invalidate() (documented
+    in drnb200/model.py), caught automatically by verify_weights=True"""
+    model, sd, x = _gate_case("drn_d_22", 64, 128, 1, False, "fp16", seed=10)
+    xd = x.to(dev())
+    a = model.predict(xd)
+    v0 = model.layer[8][0].weight._version
+    model.layer[8][0].weight.data.mul_(0.0)
+    assert model.layer[8][0].weight._version == v0                 # the premise: no version bump
+    assert torch.equal(model.predict(xd), a)                       # stale by design
+    model.invalidate()
+    b = model.predict(xd)
+    op = [o for o in model.engine().ops if o.key == "layer.8.0"][0]
+    assert op.n_live == 0 and not torch.equal(a, b)
+    # BN edits through .data and prepare(force=True)
+    model.layer[7][1].weight.data.fill_(0.0)
+    model.prepare(force=True)
+    c = model.predict(xd)
+    assert not torch.equal(b, c)
+    # verify_weights=True: no invalidate() needed
+    m2 = drnb200.DRNSeg("drn_d_22", 19, pretrained=False, verify_weights=True)
+    m2.load_state_dict(sd, strict=False)
+    m2 = m2.to(dev()).eval()
+    a2 = m2.predict(xd)
+    assert torch.equal(a2, a)
+    m2.layer[8][0].weight.data.mul_(0.0)
+    assert torch.equal(m2.predict(xd), b)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_frames_on_another_device_and_data_parallel():
+    """frames on cuda:1 while cuda:0 is the current device run on cuda:1 (per-device engines, device guard), and
+    nn.DataParallel(DRNSeg) — the reference's multi-GPU wrapper, semantic_seg.py:812 — gives the single-GPU result"""
+    model, sd, x = _gate_case("drn_d_22", 64, 128, 4, True, "fp16", seed=13)
+    x0 = x.to("cuda:0")
+    with torch.no_grad():
+        ref_lp, ref_seg = model(x0)
+        ref_lab = model.predict(x0)
+        assert torch.cuda.current_device() == 0
+        lab1 = model.predict(x.to("cuda:1"))
+        assert lab1.device.index == 1 and torch.equal(lab1.cpu(), ref_lab.cpu())
+        assert set(model._engines) == {0, 1}
+        dp = torch.nn.DataParallel(model, device_ids=[0, 1])
+        lp, seg = dp(x0)
+    assert torch.equal(lp.cpu(), ref_lp.cpu()) and torch.equal(seg.cpu(), ref_seg.cpu())
+    assert set(model._engines) == {0, 1}                           # replicas reused the original's engines
 
 
 def test_input_validation():
@@ -648,8 +761,8 @@ def test_eval_loop_mirrors_of_test_and_val_miou(tmp_path):
 
 
 def test_full_size_properties():
-    """BASELINE size (1024x2048): size-independent properties instead of a minutes-long CPU oracle run:
-    (i) tcgen05 and CUDA-core direct kernels agree layer for layer on the same tile lists,
+    """BASELINE size (1024x2048), beside test_parity_gates_at_benchmark_size: size-independent properties
+    (i) tcgen05 and CUDA-core direct kernels agree on the same tile lists,
     (ii) frames are independent: predict(batch)[i] == predict(frame i),
     (iii) determinism: two runs are bit-identical, (iv) the label histogram sums to the pixel count."""
     model, sd, x = _gate_case("drn_d_22", 1024, 2048, 2, True, "fp16", seed=12)

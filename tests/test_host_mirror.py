@@ -77,8 +77,36 @@ def test_cuda_path_fails_loudly_without_gpu_input():
     m = drnb200.DRNSeg("drn_d_22", 19, pretrained=False)
     with pytest.raises(ffi.Drnb200Error):
         m(torch.zeros(1, 3, 64, 64))          # CPU tensor: there is no CPU fallback
-    with pytest.raises(RuntimeError):
-        drnb200.DRNSeg("drn_d_22", 19)        # pretrained=True needs the model zoo
+    # the reference's signature default pretrained=True (semantic_seg.py:127, the training call passes it too): no
+    # model-zoo download here, so it warns and keeps the random initialisation instead of failing
+    with pytest.warns(UserWarning, match="pretrained=True"):
+        m2 = drnb200.DRNSeg("drn_d_22", 19)
+    assert list(m2.state_dict().keys()) == list(m.state_dict().keys())
+    # inference only: train mode with gradients enabled raises a targeted error instead of returning eval results
+    m.train()
+    with pytest.raises(ffi.Drnb200Error, match="inference path"):
+        m(torch.zeros(1, 3, 64, 64))
+    # the fused head hard-codes the analytic bilinear kernel: a checkpoint with a different `up.weight` is refused
+    m.eval()
+    with torch.no_grad():
+        m.up.weight[3, 0, 5, 5] += 0.25
+    with pytest.raises(ffi.Drnb200Error, match="fill_up_weights"):
+        m.engine(torch.device("cpu"))
+
+
+def test_module_copies_do_not_share_engines():
+    """copy.deepcopy (and pickling) of the mirror must not duplicate raw plan handles; DataParallel-style shallow
+    replicas DO share the original's per-device engines"""
+    import copy
+    m = drnb200.DRNSeg("drn_d_22", 19, pretrained=False)
+    eng = m.engine(torch.device("cpu"))
+    c = copy.deepcopy(m)
+    assert c._engines == {} and c._origin() is c and c.engine(torch.device("cpu")) is not eng
+    assert c.engine(torch.device("cpu")).m is c
+    replica = m._replicate_for_data_parallel()
+    assert replica._engines is m._engines and replica._origin() is m
+    assert replica.engine(torch.device("cpu")) is eng and eng.m is m
+    assert m.act_dtype_default == "fp16"
 
 
 BLOCK_CASES = {

@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/drnb200.h"
 
 namespace drnb200 {
@@ -24,6 +25,20 @@ int  cuda_fail(cudaError_t e, const char* what);
   do {                                                                   \
     if (!(cond)) { drnb200::set_error(__VA_ARGS__); return DRNB200_E_ARG; } \
   } while (0)
+
+// Diagnostic knobs that make results INVALID (DRNB200_DBG timing probes, DRNB200_HALO=1) exist only in a
+// `make EXTRA=-DDRNB200_DIAG` build: the shipping library never reads them, so a stray variable in a job's
+// environment cannot silently corrupt a forward.  The routing A/B knobs (DRNB200_ROW, _NG, _GATHER, _HEAD, ...)
+// select between correct implementations and stay available.
+inline int diag_env(const char* name) {
+#ifdef DRNB200_DIAG
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+#else
+  (void)name;
+  return 0;
+#endif
+}
 
 // ------------------------------------------------------------------ 16-bit storage helpers
 template <int DT> struct Act;  // DT = DRNB200_BF16 / DRNB200_F16

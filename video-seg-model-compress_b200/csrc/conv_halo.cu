@@ -331,7 +331,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 h_encode_fn() {
 }
 
 bool conv_halo_supported(const drnb200_conv_desc& d) {
-  // DRNB200_HALO=0 disables the path (A/B measurements); 1 = set the descriptor base offset (diagnostic, wrong)
+  // DRNB200_HALO=0 disables the path (A/B measurements); in -DDRNB200_DIAG builds 1 = set the descriptor base offset
+  // (reproduces the wrong-swizzle finding of DESIGN.md section 3)
   static const char* env = getenv("DRNB200_HALO");
   if (env && env[0] == '0') return false;
   return d.ksize == 3 && d.stride == 1 && d.dilation >= 1 && d.dilation <= 4 && d.Cin == d.tile_ci &&
@@ -364,10 +365,10 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   p.magic_x = p.tiles_x == 1 ? 0u : (uint32_t)(((1ull << 32) + p.tiles_x - 1) / p.tiles_x);
   p.magic_y = p.tiles_y == 1 ? 0u : (uint32_t)(((1ull << 32) + p.tiles_y - 1) / p.tiles_y);
   p.idesc = umma_idesc_f16(128, c.Cout, d.act_dtype);
-  static const char* env = getenv("DRNB200_HALO");
-  p.base_off_mode = (env && env[0] == '1') ? 1u : 0u;
-  static const char* envd = getenv("DRNB200_DBG");
-  p.dbg = envd ? atoi(envd) : 0;
+  static const int env_halo = diag_env("DRNB200_HALO");
+  p.base_off_mode = env_halo == 1 ? 1u : 0u;
+  static const int envd = diag_env("DRNB200_DBG");
+  p.dbg = envd;
   const size_t kMaxSmem = 232448;
   const size_t fixed = 1024 + ((9u * p.w_tile_bytes + 1023u) & ~1023u) + sizeof(HSync);
   p.ring = (int)std::min<size_t>(H_MAX_RING, (kMaxSmem - fixed) / p.halo_bytes);

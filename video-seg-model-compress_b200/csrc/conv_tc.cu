@@ -658,9 +658,9 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   // ---- ROW variant: 3x3 stride-1 convs over 64-channel K-blocks whose tile is one 256-pixel row segment
   static const char* env_row = getenv("DRNB200_ROW");       // A/B knob: "0" keeps the per-tap pipeline
   p.row_mode = 0;
-  static const char* env_dbg = getenv("DRNB200_DBG");        // timing diagnostics of the ROW mainloop (results invalid):
-  p.dbg = env_dbg ? atoi(env_dbg) : 0;                       // 1 no weight loads, 2 no row loads, 4 no residual loads,
-                                                             // 8 no output stores, 16 no epilogue math / staging writes
+  static const int env_dbg = diag_env("DRNB200_DBG");        // -DDRNB200_DIAG builds only: timing diagnostics of the ROW
+  p.dbg = env_dbg;                                           // mainloop (results invalid): 1 no weight loads, 2 no row loads,
+                                                             // 4 no residual loads, 8 no output stores, 16 no epilogue math
   if (mode == MODE_T && p.taps == 9 && d.stride == 1 && p.tile_ci == 64 && d.dilation <= 4 && TW == kRowPx &&
       TH == 1 && !(env_row && env_row[0] == '0')) {
     static const char* env_ring = getenv("DRNB200_ROW_RING");   // "x,w" ring sizes for tuning

@@ -427,8 +427,8 @@ int stem_tx_forward(StemTxState* s, const void* x, int src_kind, const uint16_t*
   p.magic_x = p.pairs_x == 1 ? 0u : (uint32_t)(((1ull << 32) + p.pairs_x - 1) / p.pairs_x);
   p.magic_y = p.tiles_y == 1 ? 0u : (uint32_t)(((1ull << 32) + p.tiles_y - 1) / p.tiles_y);
   p.idesc = umma_idesc_f16(128, 128, act_dtype);
-  static const char* envd = getenv("DRNB200_DBG");
-  p.dbg = envd ? atoi(envd) : 0;
+  static const int envd = diag_env("DRNB200_DBG");
+  p.dbg = envd;
   auto fn = tx_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return DRNB200_E_CUDA; }
   cuuint32_t estr[4] = {1, 1, 1, 1};

@@ -138,9 +138,9 @@ class ConvLayer:
         c = self.conv
         return c.out_channels * c.in_channels * c.kernel_size[0] ** 2
 
-    def refresh(self, mask_dict, act_dtype, device):
+    def refresh(self, mask_dict, act_dtype, device, stamp=()):
         """(re)build tile list, packed weights and BN affine if the parameters changed"""
-        ver = self.version_key(mask_dict) + (act_dtype, str(device))
+        ver = self.version_key(mask_dict) + (act_dtype, str(device), stamp)
         if ver == self.version:
             return False
         lib = ffi.lib()
@@ -265,6 +265,7 @@ class ProjResidualConv(ConvLayer):
     keeps the [conv1 | downsample] form.  Only the row-halo kernel runs this (feature maps wider than 128 pixels)."""
 
     MAX_RATIO = 1024.0
+    MAX_SUBNORMAL_FRACTION = 1e-3     # of the live rescaled shortcut weights (random-init Gaussians: ~1e-4 at ratio 1)
 
     def __init__(self, key, block, input_from, proj_from, proj_pitch):
         super().__init__(key + ".conv2", block.conv2, block.bn2, True, residual_from=proj_from,
@@ -306,8 +307,8 @@ class ProjResidualConv(ConvLayer):
                                            ffi.ptr(kblk), act_dtype, ffi.ptr(packed), st), "pack_weights(%s)" % self.key)
         return row_ptr.cpu().tolist(), kblk[:n], packed[:n], n
 
-    def refresh(self, mask_dict, act_dtype, device):
-        ver = self.version_key(mask_dict) + (act_dtype, str(device))
+    def refresh(self, mask_dict, act_dtype, device, stamp=()):
+        ver = self.version_key(mask_dict) + (act_dtype, str(device), stamp)
         if ver == self.version:
             return False
         self.destroy_plans()
@@ -318,6 +319,14 @@ class ProjResidualConv(ConvLayer):
         ratio = sd / s2
         if not bool(torch.isfinite(ratio).all()) or float(ratio.abs().max()) > self.MAX_RATIO:
             raise ProjFallback(self.key)
+        if act_dtype == ffi.F16:
+            # fp16 has 5 exponent bits: rescaled shortcut weights below 2^-14 would be rounded as subnormals (or to
+            # zero) and the lost relative precision is multiplied back by s2 in the epilogue; above 65504 they overflow
+            folded = (wd * md.ne(0)).abs() * ratio.abs().view(-1, 1, 1, 1)
+            live = folded[folded > 0]
+            if live.numel() and (float(live.max()) > 6.0e4 or
+                                 float((live < 2.0 ** -14).float().mean()) > self.MAX_SUBNORMAL_FRACTION):
+                raise ProjFallback(self.key)
         self.tile_o, self.tile_ci = 128, 64
         rp2, kb2, pk2, n2 = self._compact_and_pack(w2, m2, act_dtype, device)
         rpd, kbd, pkd, nd = self._compact_and_pack((wd * ratio.view(-1, 1, 1, 1)).contiguous(), md, act_dtype, device)
@@ -408,8 +417,11 @@ def ingest_lut(mean, std, act_dtype):
 class Engine:
     """builds and runs the launch list for one DRNSeg module"""
 
-    def __init__(self, seg_module, act_dtype="bf16", conv_impl=ffi.IMPL_AUTO, fuse_downsample=True):
+    def __init__(self, seg_module, act_dtype="fp16", conv_impl=ffi.IMPL_AUTO, fuse_downsample=True,
+                 verify_weights=False):
         self.m = seg_module
+        self.verify_weights = verify_weights      # fingerprint parameter CONTENTS on every call (catches `.data` writes)
+        self.epoch = 0                            # bumped by invalidate(); part of every cache key
         self.fuse_downsample = fuse_downsample    # [conv1 | 1x1 downsample] of a BasicBlock in one launch
         self.act_dtype = _DT[act_dtype] if isinstance(act_dtype, str) else int(act_dtype)
         self.conv_impl = conv_impl
@@ -550,14 +562,33 @@ class Engine:
         """attach a Pruner.mask_dict (pruners/Pruner.py:13); None = derive liveness from zeros"""
         self.mask_dict = mask_dict
 
+    def invalidate(self):
+        """drop every derived cache on the next call (parameter writes through `.data` bypass the version counters)"""
+        self.epoch += 1
+
+    def _stamp(self):
+        """cache-key component: the invalidate() epoch, plus (verify_weights) a content fingerprint of all parameters
+        and buffers — one device reduction per tensor and ONE host synchronisation per call"""
+        if not self.verify_weights:
+            return (self.epoch,)
+        sums = [t.detach().double().abs().sum() + t.detach().double().sum() * 0.5
+                for t in list(self.m.parameters()) + list(self.m.buffers()) if t.is_floating_point()]
+        if self.mask_dict is not None:
+            sums += [m.detach().double().sum() for m in self.mask_dict.values()]
+        by_dev = {}
+        for v in sums:
+            by_dev.setdefault(v.device, []).append(v)
+        return (self.epoch,) + tuple(x for vs in by_dev.values() for x in torch.stack(vs).cpu().tolist())
+
     def refresh(self, device, ops=None):
         rebuilt = 0
+        stamp = self._stamp()
         for op in (self.ops if ops is None else ops):
-            rebuilt += bool(op.refresh(self.mask_dict, self.act_dtype, device))
+            rebuilt += bool(op.refresh(self.mask_dict, self.act_dtype, device, stamp))
         conv, bn, _ = self.stem
         stem_w, stem_wver = _effective_weight(conv)
         ver = (stem_wver, bn.weight._version, bn.bias._version, bn.running_mean._version,
-               bn.running_var._version, str(device))
+               bn.running_var._version, str(device), stamp)
         if getattr(self, "_stem_version", None) != ver:
             inv = torch.rsqrt(bn.running_var.detach().to(device, torch.float32) + bn.eps)
             self.stem_scale = (bn.weight.detach().to(device, torch.float32) * inv).contiguous()
@@ -569,7 +600,7 @@ class Engine:
             self._drop_stem_plans()
         seg = self.m.seg
         seg_w, seg_wver = _effective_weight(seg)
-        hver = (seg_wver, seg.bias._version, self.act_dtype, str(device))
+        hver = (seg_wver, seg.bias._version, self.act_dtype, str(device), stamp)
         if self.head_version != hver:
             lib = ffi.lib()
             for p in self.head_plans.values():
@@ -645,11 +676,23 @@ class Engine:
         return dense + seg, live + seg, tile + seg
 
     # ---- forward ---------------------------------------------------------------------------------
-    def run(self, x, want_labels=True, want_logprob=False, want_seg=False, timings=None):
+    def run(self, x, want_labels=True, want_logprob=False, want_seg=False, timings=None, taps=None):
         """launch the whole path on the current stream.  `timings`, if a list, receives
-        (name, start_event, end_event) per launch group (CUDA events on the launching stream)."""
+        (name, start_event, end_event) per launch group (CUDA events on the launching stream).
+        `taps`, if a dict, receives a float32 NCHW copy of every stored activation keyed by the state_dict prefix of
+        the conv that produced it (the keys of the oracle's taps; a fused [conv1 | downsample] launch yields both)."""
         def timed(name):
             return _Timed(name, timings)
+
+        tdt = torch.bfloat16 if self.act_dtype == ffi.BF16 else torch.float16
+
+        def tap(op_keys, buf, n, oh, ow, ch):
+            if taps is None:
+                return
+            t = buf[:n * oh * ow * ch].view(tdt).view(n, oh, ow, ch).float().permute(0, 3, 1, 2)
+            step = ch // len(op_keys)
+            for j, k in enumerate(op_keys):
+                taps[k] = t[:, j * step:(j + 1) * step].contiguous()
 
         u8 = x.dtype == torch.uint8
         if u8:
@@ -674,6 +717,12 @@ class Engine:
         # seg_video_old.py:127)
         if W % 4 or H < 8 or W < 8:
             raise ffi.Drnb200Error("W must be a multiple of 4 and H, W >= 8 (got %dx%d)" % (H, W))
+        # every launch, allocation and stream query below must target the input's device, whatever the caller's
+        # current device is (frames on cuda:1 while cuda:0 is current, DataParallel worker threads)
+        with torch.cuda.device(x.device):
+            return self._run(x, u8, N, H, W, want_labels, want_logprob, want_seg, timed, tap)
+
+    def _run(self, x, u8, N, H, W, want_labels, want_logprob, want_seg, timed, tap):
         x = x.contiguous()
         dev = x.device
         lib = ffi.lib()
@@ -681,7 +730,13 @@ class Engine:
         try:
             self.refresh(dev, ops)
         except ProjFallback:
-            self.ops_proj = None               # ill-conditioned BatchNorm fold: keep the shortcut as its own output
+            # ill-conditioned BatchNorm fold: keep the shortcut as its own output.  The alternative list's own ops
+            # (everything not shared with self.ops) may already hold plans: destroy them before dropping the list
+            shared = set(map(id, self.ops))
+            for op in self.ops_proj:
+                if id(op) not in shared:
+                    op.destroy_plans()
+            self.ops_proj = None
             ops = self.ops
             self.refresh(dev, ops)
         self.last_ops = ops
@@ -729,6 +784,7 @@ class Engine:
                           "stem_plan_forward")
         launches += 1
         outs[-1] = y
+        tap([self.stem[2]], y, N, H, W, c0)
         for i, op in enumerate(ops):
             src = op.input_from if op.input_from is not None else i - 1
             ih, iw = shapes[src]
@@ -742,6 +798,7 @@ class Engine:
                           "conv_forward(%s)" % op.key)
             launches += 1
             outs[i] = yo
+            tap(op.keys if isinstance(op, FusedFirstConv) else op.keys[:1], yo, N, oh, ow, op.out_channels)
             for j in [k for k, last in last_use.items() if last == i]:
                 give(j)
         last = len(ops) - 1

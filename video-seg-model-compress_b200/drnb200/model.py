@@ -13,9 +13,25 @@ So ``final = model(x)[0]; _, pred = torch.max(final, 1)`` of ``test()`` (semanti
 
     predict(x) -> uint8 [N,H,W]      labels straight from the fused head, no logits materialised
     set_pruner(pruner) / set_masks(mask_dict)   hand the Pruner.mask_dict to the tile-list builder
-    prepare()                        force the (tile list, packed weights) cache to be rebuilt now
+    prepare()                        build the (tile list, packed weights) cache now
+    invalidate()                     drop that cache: REQUIRED after writing parameters through ``.data``
+
+Cache coherence.  The derived device cache is keyed on the parameters' autograd version counters, which every
+in-place tensor op bumps (``state_dict()[k] *= mask`` of Pruner.apply_masks, ``load_state_dict``, optimizers
+under ``no_grad``).  Writes through ``param.data`` do NOT bump the counter; call ``invalidate()`` after them, or
+construct with ``verify_weights=True`` to re-fingerprint every parameter on every call (slow, debugging aid).
+
+Devices.  One engine per CUDA device is kept (keyed by the input's device) and every call runs under
+``torch.cuda.device(x.device)``, so ``nn.DataParallel(DRNSeg)`` (semantic_seg.py:812) works: replicas share
+the original module's per-device engines, which read the original parameters.
+
+Inference only: there is no autograd graph and BatchNorm always uses its running statistics; ``forward`` raises in
+training mode with gradients enabled instead of silently returning eval-mode results.
 """
 import math
+import threading
+import warnings
+import weakref
 
 import torch
 import torch.nn as nn
@@ -37,10 +53,19 @@ def fill_up_weights(up):
 
 
 class DRNSeg(nn.Module):
+    act_dtype_default = "fp16"       # the 16-bit storage type that passes the label gate
+
     def __init__(self, model_name, classes, pretrained_model=None, pretrained=True,
-                 use_torch_up=False, backbone_attr="layer", act_dtype="bf16"):
+                 use_torch_up=False, backbone_attr="layer", act_dtype="fp16", verify_weights=False):
+        """`act_dtype`: 16-bit activation storage, "fp16" (default: passes the label gate) or
+        "bf16".  `pretrained=True` is the reference's signature default (ImageNet weights from its model zoo,
+        drn.py:13-24); there is no download here, so it warns and keeps the random initialisation — load a
+        checkpoint with load_state_dict / drnb200.checkpoint afterwards."""
         super().__init__()
-        model = _drn.build(model_name, pretrained=pretrained, num_classes=1000)
+        if pretrained:
+            warnings.warn("DRNSeg(pretrained=True): the reference's model-zoo download (drn.py:13-24) is not available; "
+                          "the backbone keeps its random initialisation - load a state_dict afterwards", stacklevel=2)
+        model = _drn.build(model_name, pretrained=False, num_classes=1000)
         if pretrained_model is not None:
             model.load_state_dict(pretrained_model)
         if backbone_attr not in ("layer", "base"):
@@ -64,13 +89,21 @@ class DRNSeg(nn.Module):
             up.weight.requires_grad = False
             self.up = up
         self._act_dtype = act_dtype
-        self._engine = None
+        self._verify_weights = bool(verify_weights)
+        # per-device engines; the dict, the lock and the weak reference to THIS module are shared by DataParallel
+        # replicas (their __dict__ is a shallow copy), so replicas run on the original module's engines
+        self._engines = {}
+        self._engine_lock = threading.Lock()
+        object.__setattr__(self, "_origin", weakref.ref(self))
         self._mask_dict = None
         self._ingest = None
 
     # ---- reference API ---------------------------------------------------------------------------
     def forward(self, x):
-        labels, logprob, seg = self._eng().run(x, want_labels=False, want_logprob=True, want_seg=True)
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.optim_parameters()):
+            raise ffi.Drnb200Error("drnb200.DRNSeg is an inference path (no autograd graph, BatchNorm running statistics); "
+                                   "call .eval() or run under torch.no_grad() - train with the reference module")
+        labels, logprob, seg = self._eng(x).run(x, want_labels=False, want_logprob=True, want_seg=True)
         return logprob, seg
 
     def optim_parameters(self, memo=None):
@@ -84,20 +117,20 @@ class DRNSeg(nn.Module):
     def predict(self, x):
         """uint8 label map [N,H,W] == torch.max(model(x)[0], 1)[1] of the reference, without ever
         writing the [N,classes,H,W] logits."""
-        return self._eng().run(x, want_labels=True)[0]
+        return self._eng(x).run(x, want_labels=True)[0]
 
     def set_ingest(self, mean, std, bgr=False):
         """enable uint8 HWC frames [N,H,W,3] as input of forward()/predict(): ToTensorVideoImage + Normalize
         (data_transforms.py:109-125, :256-281; mean/std from info.json) are fused into the stem kernel."""
         self._ingest = (mean, std, bgr)
-        if self._engine is not None:
-            self._engine.set_ingest(mean, std, bgr)
+        for eng in self._engines.values():
+            eng.set_ingest(mean, std, bgr)
         return self
 
     def set_masks(self, mask_dict):
         self._mask_dict = mask_dict
-        if self._engine is not None:
-            self._engine.set_masks(mask_dict)
+        for eng in self._engines.values():
+            eng.set_masks(mask_dict)
         return self
 
     def set_pruner(self, pruner):
@@ -106,19 +139,35 @@ class DRNSeg(nn.Module):
     def set_act_dtype(self, act_dtype):
         if act_dtype != self._act_dtype:
             self._act_dtype = act_dtype
-            if self._engine is not None:
-                self._engine.close()
-                self._engine = None
+            self._close_engines()
         return self
 
-    def prepare(self, device=None):
-        dev = device or next(self.parameters()).device
-        return self._eng().refresh(torch.device(dev))
+    def prepare(self, device=None, force=False):
+        """build (or, with force=True, rebuild from scratch) the device-side cache for `device` now"""
+        dev = torch.device(device or next(self.parameters()).device)
+        if force:
+            self.invalidate()
+        with torch.cuda.device(dev):
+            return self._eng(dev).refresh(dev)
 
-    def engine(self):
-        return self._eng()
+    def invalidate(self):
+        """forget every derived cache (tile lists, packed weights, BN affines, head/stem weights).  Needed after
+        parameter writes that bypass the autograd version counter (``p.data.mul_()``, ``p.data = ...``)."""
+        for eng in self._engines.values():
+            eng.invalidate()
+        return self
 
-    def _eng(self):
+    def engine(self, device=None):
+        return self._eng(device)
+
+    def _close_engines(self):
+        with self._engine_lock:
+            for eng in self._engines.values():
+                eng.close()
+            self._engines.clear()
+
+    def _eng(self, where=None):
+        """engine of the CUDA device `where` (a tensor, a device, or None = the parameters' device)"""
         if self.use_torch_up:
             raise ffi.Drnb200Error("use_torch_up=True (UpsamplingBilinear2d, align_corners) is not part "
                                    "of the accelerated path; the reference's default is the fixed "
@@ -126,17 +175,61 @@ class DRNSeg(nn.Module):
         up = self.up.weight
         if tuple(up.shape[2:]) != (16, 16) or self.up.stride != (8, 8) or self.up.padding != (4, 4):
             raise ffi.Drnb200Error("`up` must be ConvTranspose2d(k=16, s=8, p=4)")
-        if self._engine is None:
-            ffi.lib()                      # fail loudly if the CUDA library is missing
-            self._engine = Engine(self, act_dtype=self._act_dtype)
-            self._engine.set_masks(self._mask_dict)
-            if self._ingest is not None:
-                self._engine.set_ingest(*self._ingest)
-        return self._engine
+        if isinstance(where, torch.Tensor):
+            where = where.device
+        dev = torch.device(where) if where is not None else next(self.parameters()).device
+        key = dev.index if dev.type == "cuda" and dev.index is not None else (
+            torch.cuda.current_device() if dev.type == "cuda" and torch.cuda.is_available() else -1)
+        eng = self._engines.get(key)
+        if eng is None:
+            with self._engine_lock:
+                eng = self._engines.get(key)
+                if eng is None:
+                    ffi.lib()                      # fail loudly if the CUDA library is missing
+                    if not torch.equal(up.detach()[:, 0].cpu().double(), _bilinear_kernel(up.shape[0], 16)):
+                        raise ffi.Drnb200Error(
+                            "`up.weight` differs from fill_up_weights (semantic_seg.py:115-124): the fused head "
+                            "hard-codes the analytic bilinear kernel and would ignore this checkpoint's values")
+                    origin = self._origin() or self
+                    eng = Engine(origin, act_dtype=self._act_dtype, verify_weights=self._verify_weights)
+                    eng.set_masks(self._mask_dict)
+                    if self._ingest is not None:
+                        eng.set_ingest(*self._ingest)
+                    self._engines[key] = eng
+        return eng
+
+    def __getstate__(self):
+        # copy.deepcopy / pickling: engines hold raw plan handles and must not be duplicated
+        state = dict(self.__dict__)
+        for k in ("_engines", "_engine_lock", "_origin"):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._engines = {}
+        self._engine_lock = threading.Lock()
+        object.__setattr__(self, "_origin", weakref.ref(self))
 
     def __del__(self):
         try:
-            if self._engine is not None:
-                self._engine.close()
+            origin = self._origin()
+            if origin is None or origin is self:       # replicas do not own the engines
+                for eng in self._engines.values():
+                    eng.close()
         except Exception:
             pass
+
+
+_UP_CACHE = {}
+
+
+def _bilinear_kernel(classes, k):
+    """[classes, k, k] float64 -> what fill_up_weights writes (as float32 values)"""
+    key = (classes, k)
+    if key not in _UP_CACHE:
+        f = math.ceil(k / 2)
+        c = (2 * f - 1 - f % 2) / (2.0 * f)
+        ax = torch.tensor([1 - abs(i / f - c) for i in range(k)], dtype=torch.float64)
+        _UP_CACHE[key] = torch.outer(ax, ax).to(torch.float32).double().expand(classes, k, k)
+    return _UP_CACHE[key]
