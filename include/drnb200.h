@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRNB200_VERSION 105
+#define DRNB200_VERSION 106
 
 /* error codes */
 #define DRNB200_OK          0
@@ -129,9 +129,11 @@ int  drnb200_conv_forward(drnb200_conv_plan* plan, const void* x_nhwc, const voi
                           void* y_nhwc, void* stream);
 /* what the plan resolved to: 1 = direct (CUDA cores), 2 = tcgen05 */
 int  drnb200_conv_plan_impl(const drnb200_conv_plan* plan);
-/* which tcgen05 kernel: 0 = conv_tc MODE_T (128-cout tiles, staged epilogue), 1 = conv_tc MODE_P (pixels as M),
- * 2 = conv_tc MODE_T with float32 output, 3 = conv_gather (im2col in smem), 4 = conv_halo (shifted windows);
- * -1 for direct plans */
+/* which tcgen05 kernel: 0 = conv_tc MODE_T (128-cout tiles, staged epilogue, one TMA box per K-block),
+ * 1 = conv_tc MODE_P (pixels as M), 2 = conv_tc MODE_T with float32 output, 3 = conv_gather (im2col in smem),
+ * 4 = conv_halo (shifted windows of one halo tile), 5 = conv_tc MODE_T ROW variant (3x3 stride 1, 64-channel K-blocks,
+ * rows wider than 128 pixels: each input row loaded once, the three kx taps as shifted UMMA windows; the only kernel
+ * that accepts proj_cin); -1 for direct plans */
 int  drnb200_conv_plan_mode(const drnb200_conv_plan* plan);
 /* live multiply-accumulates of one forward (tile-list granularity) — the numerator of tensor-pipe
  * utilisation counted at block granularity; element-granularity MACs are computed by the host. */
@@ -142,9 +144,12 @@ void drnb200_conv_plan_destroy(drnb200_conv_plan* plan);
  * x: float32 NCHW [N,3,H,W] exactly as the callers feed DRNSeg.forward (semantic_seg.py:444);
  * w: float32 OIHW [C0,3,7,7]; y: act_dtype NHWC [N,H,W,C0].  C0 must be 16.
  * Two implementations:
- *   drnb200_stem_plan_*    tcgen05: the 128-pixel x 160 im2col tile is gathered from the fp32 frame,
- *                          converted to act_dtype and multiplied on the tensor cores (weights rounded to
- *                          act_dtype once at plan creation); this is what DRNSeg uses.
+ *   drnb200_stem_plan_*    tcgen05, no im2col: the x direction of the 7x7 window is folded into a banded (Toeplitz)
+ *                          weight matrix built once at plan creation (weights rounded to act_dtype), the y
+ *                          direction is a row shift of the A operand inside one 16-bit halo tile that TMA loads
+ *                          from the fp32 frame and the convert warps round to act_dtype (21 MMAs of
+ *                          M=128 rows x N=128 (8 columns x 16 couts) x K=16 per 1024 pixels); this is what
+ *                          DRNSeg uses.
  *   drnb200_stem_forward   CUDA-core fp32 direct convolution (no input/weight rounding); kept as the
  *                          full-precision cross-check of the tensor-core stem. */
 typedef struct drnb200_stem_plan drnb200_stem_plan;
@@ -212,6 +217,21 @@ int drnb200_confusion(const uint8_t* pred, const void* label, int label_is_i64, 
 int drnb200_colorize(const uint8_t* labels, int64_t n_px, const uint8_t* palette, int n_colors,
                      const uint8_t* frames_or_null, float alpha, uint8_t* out_rgb, void* stream);
 int drnb200_labels_to_i64(const uint8_t* labels, int64_t n, int64_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pinned HOST staging buffers for frames (H2D) and label maps (D2H) — the two PCIe ends of the path.  Replaces the
+ * pageable tensors + `.cuda()` / `.cpu()` of the reference's callers (semantic_seg.py:440-455, seg_video_new.py).
+ * HOST functions; the pointer is valid on every device (portable).  mode:
+ *   DRNB200_HOST_PINNED  cudaHostAlloc                                   (== torch pin_memory())
+ *   DRNB200_HOST_WC      write-combined: DMA reads skip CPU-cache snooping; CPU reads of it are very slow -> frames only
+ *   DRNB200_HOST_HUGE    2 MiB-aligned anonymous mapping, MADV_HUGEPAGE, cudaHostRegister: fewer IOMMU entries per copy
+ * drnb200_host_free accepts only pointers returned by drnb200_host_alloc (DRNB200_E_ARG otherwise).
+ * ------------------------------------------------------------------------------------------- */
+#define DRNB200_HOST_PINNED 0
+#define DRNB200_HOST_WC     1
+#define DRNB200_HOST_HUGE   2
+int drnb200_host_alloc(void** out, uint64_t bytes, int mode);
+int drnb200_host_free(void* p);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-scale test.  Replaces resize_4d_tensor (semantic_seg.py:471-504: every float32 plane through

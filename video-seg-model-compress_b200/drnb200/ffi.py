@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libdrnb200.so")
 
 BF16, F16 = 0, 1
 IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05 = 0, 1, 2
+HOST_PINNED, HOST_WC, HOST_HUGE = 0, 1, 2
 KB_PROJ = 3 << 20        # DRNB200_KB_PROJ: tile-list entries of the residual projection (include/drnb200.h)
 
 
@@ -61,6 +62,8 @@ SIGNATURES = {
     "drnb200_ms_accumulate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
                                         _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]),
     "drnb200_ms_argmax": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "drnb200_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64, C.c_int]),
+    "drnb200_host_free": (C.c_int, [_P]),
 }
 
 _lib = None

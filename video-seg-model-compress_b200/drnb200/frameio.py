@@ -68,3 +68,39 @@ def colorize(labels, palette=CITYSCAPE_PALETTE):
 def overlay(labels, frames, alpha=0.6, palette=CITYSCAPE_PALETTE):
     """rint(alpha * palette[labels] + (1 - alpha) * frames), uint8 RGB"""
     return _colorize(labels, frames, alpha, palette)
+
+
+class HostBuffer:
+    """Pinned host staging buffer for frames (H2D) or label maps (D2H), allocated by the library
+    (`drnb200_host_alloc`): ``mode`` = "pinned" (cudaHostAlloc, what ``Tensor.pin_memory()`` gives), "wc"
+    (write-combined: DMA reads skip CPU-cache snooping; never read it from the CPU — frames only) or "huge"
+    (2 MiB-aligned MADV_HUGEPAGE mapping registered with CUDA: fewer IOMMU entries per copy).
+    ``.tensor`` is a torch view of the memory; it must not outlive the buffer (``close()`` / garbage collection)."""
+
+    MODES = {"pinned": ffi.HOST_PINNED, "wc": ffi.HOST_WC, "huge": ffi.HOST_HUGE}
+
+    def __init__(self, shape, dtype=torch.uint8, mode="pinned"):
+        import ctypes as C
+        if mode not in self.MODES:
+            raise ffi.Drnb200Error("HostBuffer mode must be one of %s" % sorted(self.MODES))
+        self.mode = mode
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        if nbytes <= 0:
+            raise ffi.Drnb200Error("HostBuffer needs a non-empty shape")
+        p = C.c_void_p()
+        ffi.check(ffi.lib().drnb200_host_alloc(C.byref(p), nbytes, self.MODES[mode]), "host_alloc(%s)" % mode)
+        self.ptr, self.nbytes = p.value, nbytes
+        raw = (C.c_uint8 * nbytes).from_address(self.ptr)
+        self.tensor = torch.frombuffer(raw, dtype=torch.uint8).view(dtype).view(*shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.tensor = None
+            ffi.lib().drnb200_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
