@@ -154,6 +154,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for roles that are NOT on the critical path (a producer waiting for a free ring slot, a stage waiting for
+// its consumer): back off with nanosleep between polls so that the polling loop does not take issue slots from the
+// warps that do the arithmetic (measured in head_fused_kernel: 1.6 M try_wait iterations = 14 % of all instructions).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 128) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) { __trap(); }
+  }
+}
+
 // ---- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(desc) : "memory");

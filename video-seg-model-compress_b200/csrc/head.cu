@@ -82,6 +82,13 @@ __device__ __forceinline__ void up_vertical(const float* at, int row_pitch, int 
       }
   }
 }
+// horizontal pass: the two taps of an output column always sum to one (w[k] + w[k+8] = 1 for k = 0..7), so
+//   out = w0*V0 + w1*V1 = V1 + w0*(V0 - V1)
+// is evaluated as ONE fma per (pixel, class) on D = V0 - V1, computed once per class for all pixels of the thread
+// (zero padding is already in V0/V1: rows and columns outside the map were staged as zeros).  Every kernel of this
+// file goes through up_h(), so predict() and forward() see bit-identical values.
+__device__ __forceinline__ float up_h(int k, float d, float v1) { return __fmaf_rn(up_w(k), d, v1); }
+
 // horizontal pass + argmax of 4 adjacent pixels (same 2x2 low-res neighbourhood): labels packed into 4 bytes;
 // strict > : the first maximum wins like torch.max
 template <int CLS_MAX>
@@ -90,13 +97,12 @@ __device__ __forceinline__ uint32_t up_argmax4(const float (&V0)[CLS_MAX], const
   uint32_t packed = 0;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const float wx0 = up_w(kx + t), wx1 = up_w(kx + t + 8);
     float best = -INFINITY;
     int arg = 0;
 #pragma unroll
     for (int c = 0; c < CLS_MAX; ++c) {
       if (c < classes) {
-        const float v = __fmaf_rn(wx1, V1[c], __fmul_rn(wx0, V0[c]));
+        const float v = up_h(kx + t, __fsub_rn(V0[c], V1[c]), V1[c]);
         if (v > best) { best = v; arg = c; }
       }
     }
@@ -149,11 +155,10 @@ up_argmax_kernel(const float* __restrict__ L, int N, int h, int w, int classes,
   if (logprob != nullptr) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const float wx0 = up_w(kx + t), wx1 = up_w(kx + t + 8);
       float s = 0.f;
 #pragma unroll
       for (int c = 0; c < CLS_MAX; ++c)
-        if (c < classes) s += expf(__fmaf_rn(wx1, V1[c], __fmul_rn(wx0, V0[c])) - best4[t]);
+        if (c < classes) s += expf(up_h(kx + t, __fsub_rn(V0[c], V1[c]), V1[c]) - best4[t]);
       lse[t] = best4[t] + logf(s);
     }
   }
@@ -164,10 +169,11 @@ up_argmax_kernel(const float* __restrict__ L, int N, int h, int w, int classes,
     for (int c = 0; c < CLS_MAX; ++c) {
       if (c < classes) {
         float4 o;
-        o.x = __fmaf_rn(up_w(kx + 8), V1[c], __fmul_rn(up_w(kx + 0), V0[c])) - lse[0];
-        o.y = __fmaf_rn(up_w(kx + 9), V1[c], __fmul_rn(up_w(kx + 1), V0[c])) - lse[1];
-        o.z = __fmaf_rn(up_w(kx + 10), V1[c], __fmul_rn(up_w(kx + 2), V0[c])) - lse[2];
-        o.w = __fmaf_rn(up_w(kx + 11), V1[c], __fmul_rn(up_w(kx + 3), V0[c])) - lse[3];
+        const float d = __fsub_rn(V0[c], V1[c]);
+        o.x = up_h(kx + 0, d, V1[c]) - lse[0];
+        o.y = up_h(kx + 1, d, V1[c]) - lse[1];
+        o.z = up_h(kx + 2, d, V1[c]) - lse[2];
+        o.w = up_h(kx + 3, d, V1[c]) - lse[3];
         *reinterpret_cast<float4*>(logprob + (((size_t)n * classes + c) * H + y) * W + x0) = o;
       }
     }
@@ -177,20 +183,50 @@ up_argmax_kernel(const float* __restrict__ L, int N, int h, int w, int classes,
 // ------------------------------------------------------------------------------------------------------------
 // head_fused_kernel — (c) as ONE kernel: classifier GEMM (tcgen05, TMEM) -> low-res class logits in shared memory
 // -> fixed-bilinear x8 upsample -> argmax -> packed label stores.  Nothing but the label map is written.
-// Persistent CTAs; tile = 112 x 48 output pixels = the 16 x 8 low-resolution neighbourhood (14 x 6 interior + the
-// one-pixel apron the transposed conv reaches into) = exactly the 128 rows of one UMMA M tile.
+// Persistent CTAs.  The transposed conv makes output pixel x depend on the low-res columns j0-1 and j0 with
+// j0 = (x+4)>>3, so the natural unit is the CELL of 8x8 output pixels x = 8*j0-4 .. 8*j0+3 (same for y) that share one
+// 2x2 low-res neighbourhood.  Tile = 15 x 7 cells = 120 x 56 output pixels, whose neighbourhoods are exactly the
+// 16 x 8 low-res pixels = the 128 rows of one UMMA M tile (round 1 tiled the OUTPUT on multiples of 8 instead: 14 x 6
+// cells per 16 x 8 low-res tile, 25 % more tiles for the same frame).
 //   warp 0      TMA: per tile C/64 K-blocks, box {64 ch, 16, 8} (out-of-map pixels arrive as zeros)
 //   warp 1      MMA: D[128 px][32 classes] += A[128 x 64] * W[32 x 64]^T, classifier weights resident in smem
 //   warps 2-5   TMEM -> + bias (0 for pixels outside the map: the transposed conv pads with zeros, not with the
 //               bias) -> shared-memory logits [128 px][20]
-//   warps 6-17  upsample + argmax, one thread = 4 adjacent pixels, 4 labels per 32-bit store (rows of 112 bytes)
-constexpr int HF_LW = 16, HF_LH = 8;                  // low-res tile incl. apron
-constexpr int HF_OW = (HF_LW - 2) * 8, HF_OH = (HF_LH - 2) * 8;   // 112 x 48 output pixels
+//   warps 6-19  upsample + argmax.  One thread = the 8 pixels of one cell in one output row: the vertical
+//               interpolation of the two low-res columns (2 x 19 values) is computed ONCE per 8 pixels (round 1:
+//               once per 4), the eight horizontal weights are compile-time constants, and the labels leave as two
+//               32-bit stores.  Arithmetic per value is the same explicitly rounded sequence as up_argmax_kernel.
+constexpr int HF_LW = 16, HF_LH = 8;                  // low-res tile (UMMA M = 128 pixels)
+constexpr int HF_CX = HF_LW - 1, HF_CY = HF_LH - 1;   // 15 x 7 cells per tile
 constexpr int HF_STAGES = 6, HF_ACC = 4, HF_LBUF = 2;
-constexpr int HF_UP_WARPS = 12;
+constexpr int HF_UP_WARPS = 14;
 constexpr int HF_THREADS = (6 + HF_UP_WARPS) * 32;
 constexpr int HF_CP = 20;                             // class pitch of the staged logits (19 classes, float4 reads)
 constexpr int HF_MAX_KB = 16;                         // C <= 1024
+
+// horizontal pass + argmax for the 8 pixels of one cell (kx = 0..7 compile-time): same operations, in the same order,
+// as up_argmax4 performs for its four pixels -> bit-identical values, first maximum wins
+template <int CLS_MAX>
+__device__ __forceinline__ void up_argmax8(const float (&V0)[CLS_MAX], const float (&V1)[CLS_MAX], int classes,
+                                           uint32_t& lo, uint32_t& hi) {
+  float best[8];
+  uint32_t arg[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { best[t] = -INFINITY; arg[t] = 0u; }
+#pragma unroll
+  for (int c = 0; c < CLS_MAX; ++c) {
+    if (c < classes) {
+      const float d = __fsub_rn(V0[c], V1[c]);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float v = up_h(t, d, V1[c]);
+        if (v > best[t]) { best[t] = v; arg[t] = (uint32_t)c; }
+      }
+    }
+  }
+  lo = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+  hi = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+}
 
 struct HeadFusedParams {
   const uint8_t* w_packed;     // C/64 tiles of 32 x 64 (128-byte rows, SWIZZLE_128B)
@@ -205,6 +241,7 @@ struct __align__(16) HFSync {
   alignas(16) float bias[32];
   uint64_t full[HF_STAGES], empty[HF_STAGES], tfull[HF_ACC], tempty[HF_ACC], lfull[HF_LBUF], lempty[HF_LBUF], wfull;
   uint32_t tmem_base, pad;
+  int chunk[HF_LBUF];            // next 32-item chunk of the tile staged in logits[lb] (claimed by the upsample warps)
 };
 
 template <int DT>
@@ -227,6 +264,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
     mbar_fence_init();
   }
   if (threadIdx.x < 32) sync->bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
+  if (threadIdx.x < HF_LBUF) sync->chunk[threadIdx.x] = 0;
   if (warp == 1) {
     tmem_alloc(&sync->tmem_base, HF_ACC * 32);
     tmem_relinquish();
@@ -247,9 +285,9 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int n = t / tiles_per_frame, r = t - n * tiles_per_frame;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      const int lx0 = tx * (HF_LW - 2) - 1, ly0 = ty * (HF_LH - 2) - 1;
+      const int lx0 = tx * HF_CX - 1, ly0 = ty * HF_CY - 1;
       for (int kb = 0; kb < p.n_kb; ++kb) {
-        mbar_wait(&sync->empty[s], ph ^ 1u);
+        mbar_wait_relaxed(&sync->empty[s], ph ^ 1u, 500);
         if (elect_one()) {
           mbar_arrive_expect_tx(&sync->full[s], 16384u);
           tma_load_4d(&tmap_x, &sync->full[s], ring + s * 16384, kb * 64, lx0, ly0, n);
@@ -267,7 +305,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
     int i = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
       const int acc = i % HF_ACC;
-      mbar_wait(&sync->tempty[acc], ((uint32_t)(i / HF_ACC) & 1u) ^ 1u);
+      mbar_wait_relaxed(&sync->tempty[acc], ((uint32_t)(i / HF_ACC) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * 32u;
       for (int kb = 0; kb < p.n_kb; ++kb) {
@@ -295,9 +333,9 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
       const int acc = i % HF_ACC, lb = i % HF_LBUF;
       const int n = t / tiles_per_frame, r = t - n * tiles_per_frame;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      const int lx = tx * (HF_LW - 2) - 1 + (m & (HF_LW - 1)), ly = ty * (HF_LH - 2) - 1 + (m >> 4);
+      const int lx = tx * HF_CX - 1 + (m & (HF_LW - 1)), ly = ty * HF_CY - 1 + (m >> 4);
       const bool inside = lx >= 0 && lx < p.w && ly >= 0 && ly < p.h;
-      mbar_wait(&sync->tfull[acc], (uint32_t)(i / HF_ACC) & 1u);
+      mbar_wait_relaxed(&sync->tfull[acc], (uint32_t)(i / HF_ACC) & 1u, 64);
       tc_fence_after();
       uint32_t v[32];
       tmem_ld32(tmem_base + (uint32_t)acc * 32u + ((uint32_t)(q * 32) << 16), v);
@@ -305,7 +343,8 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sync->tempty[acc]);
-      mbar_wait(&sync->lempty[lb], ((uint32_t)(i / HF_LBUF) & 1u) ^ 1u);
+      mbar_wait_relaxed(&sync->lempty[lb], ((uint32_t)(i / HF_LBUF) & 1u) ^ 1u, 1000);   // a whole tile of slack
+      if (m == 0) sync->chunk[lb] = 0;                    // every upsample warp has left this buffer
       float* dst = &sync->logits[lb][m][0];
 #pragma unroll
       for (int c4 = 0; c4 < HF_CP / 4; ++c4) {
@@ -321,28 +360,37 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
     }
   } else {
     // ================================================================= upsample + argmax
-    const int ut = (warp - 6) * 32 + lane;              // 0 .. 383
     const int H = 8 * p.h, W = 8 * p.w;
-    constexpr int ITEMS = HF_OH * (HF_OW / 4);          // 48 rows x 28 quads
+    constexpr int ITEMS = HF_CY * 8 * HF_CX;            // 56 output rows x 15 cells
     int i = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
       const int lb = i % HF_LBUF;
       const int n = t / tiles_per_frame, r = t - n * tiles_per_frame;
       const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-      const int X0 = tx * HF_OW, Y0 = ty * HF_OH;
-      const int lx0 = tx * (HF_LW - 2) - 1, ly0 = ty * (HF_LH - 2) - 1;
+      const int X0 = tx * (HF_CX * 8) - 4, Y0 = ty * (HF_CY * 8) - 4;      // first pixel of cell (0, 0)
       mbar_wait(&sync->lfull[lb], (uint32_t)(i / HF_LBUF) & 1u);
       const float* tile = &sync->logits[lb][0][0];
-      for (int it = ut; it < ITEMS; it += HF_UP_WARPS * 32) {
-        const int yy = it / (HF_OW / 4), xq = it - yy * (HF_OW / 4);
-        const int y = Y0 + yy, x0 = X0 + 4 * xq;
-        if (y < H && x0 < W) {
-          const int i0 = (y + 4) >> 3, ky = (y + 4) & 7, j0 = (x0 + 4) >> 3, kx = (x0 + 4) & 7;
-          const int ra = i0 - ly0, ca = j0 - lx0;
-          float V0[19], V1[19], best4[4];
-          up_vertical<19>(tile + (ra * HF_LW + ca) * HF_CP, HF_LW * HF_CP, ky, V0, V1);
-          const uint32_t packed = up_argmax4<19>(V0, V1, kx, p.classes, best4);
-          *reinterpret_cast<uint32_t*>(p.labels + ((size_t)n * H + y) * W + x0) = packed;
+      // 32-item chunks are claimed dynamically: the four SM sub-partitions host different numbers of upsample warps
+      // (and the polling warps of the other roles), a static split left the slowest one 10 % behind
+      for (;;) {
+        int ck = 0;
+        if (lane == 0) ck = atomicAdd(&sync->chunk[lb], 1);
+        ck = __shfl_sync(0xffffffffu, ck, 0);
+        if (ck * 32 >= ITEMS) break;
+        const int it = ck * 32 + lane;
+        if (it < ITEMS) {
+          const int yy = it / HF_CX, cx = it - yy * HF_CX;
+          const int y = Y0 + yy, x0 = X0 + 8 * cx;
+          if (y >= 0 && y < H && x0 < W) {
+            // cell row yy>>3 reads low-res tile rows (yy>>3) and (yy>>3)+1, cell column cx reads tile columns cx, cx+1
+            float V0[19], V1[19];
+            up_vertical<19>(tile + (((yy >> 3) + 1) * HF_LW + cx + 1) * HF_CP, HF_LW * HF_CP, yy & 7, V0, V1);
+            uint32_t lo, hi;
+            up_argmax8<19>(V0, V1, p.classes, lo, hi);
+            uint8_t* row = p.labels + ((size_t)n * H + y) * W;
+            if (x0 >= 0) *reinterpret_cast<uint32_t*>(row + x0) = lo;
+            if (x0 + 4 < W) *reinterpret_cast<uint32_t*>(row + x0 + 4) = hi;
+          }
         }
       }
       __syncwarp();
@@ -460,8 +508,8 @@ static int head_fused_launch(drnb200_head_plan* plan, const void* x, uint8_t* la
   p.w_packed = reinterpret_cast<const uint8_t*>(plan->d_wpacked);
   p.bias = plan->d_shift; p.labels = labels;
   p.N = plan->N; p.h = plan->h; p.w = plan->w; p.n_kb = plan->C / 64; p.classes = plan->classes;
-  p.tiles_x = (8 * plan->w + HF_OW - 1) / HF_OW;
-  p.tiles_y = (8 * plan->h + HF_OH - 1) / HF_OH;
+  p.tiles_x = (plan->w + 1 + HF_CX - 1) / HF_CX;      // cells j0 = 0 .. w (the first and the last are half cells)
+  p.tiles_y = (plan->h + 1 + HF_CY - 1) / HF_CY;
   p.total_tiles = plan->N * p.tiles_x * p.tiles_y;
   p.idesc = umma_idesc_f16(128, HEAD_CP, plan->act_dtype);
   const size_t smem = 1024 + HF_STAGES * 16384 + (size_t)p.n_kb * 4096;
