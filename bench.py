@@ -344,27 +344,31 @@ def timed_steps(ctx, model, meter, x, gt, steps, warmup):
     return ctx.max_over_ranks([ms])[0]
 
 
-def e2e_measure(ctx, model, hx, B, H, W, steps):
+def e2e_measure(ctx, model, hx, B, H, W, steps, eval_mode=None):
     """hx: pinned host batch (float32 NCHW, or uint8 NHWC with set_ingest).  Every step copies ITS input from pinned
-    host memory (copy stream), runs predict (main stream) and copies the label map back to pinned host memory (D2H
-    stream); double buffered so the copies of step i+1 overlap the kernels of step i.
+    host memory (copy stream), runs predict (main stream) and copies the result back to pinned host memory (D2H
+    stream); three input buffers so the copies of the next steps overlap the kernels of this one.
+    The result is the uint8 label map (video mode, seg_video.py), or — `eval_mode` = (meter, gt) — the 19x19 confusion
+    matrix accumulated on the device (evaluation mode, semantic_seg.py test(): 2.9 kB per step).
     -> (ms for `steps` steps, mean H2D GB/s of this rank's copies, mean D2H GB/s)"""
     dev = ctx.dev
+    NB = 3
     copy_stream = torch.cuda.Stream(device=dev)
     d2h_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
-    hl = [torch.empty((B, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    xd = [torch.empty(hx.shape, dtype=hx.dtype, device=dev) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    d2h_done = [torch.cuda.Event() for _ in range(2)]
-    keep = [None, None]
+    hl = [torch.empty((B, H, W), dtype=torch.uint8).pin_memory() for _ in range(NB)]
+    hh = [torch.empty((19, 19), dtype=torch.int64).pin_memory() for _ in range(NB)]
+    xd = [torch.empty(hx.shape, dtype=hx.dtype, device=dev) for _ in range(NB)]
+    ready = [torch.cuda.Event() for _ in range(NB)]
+    consumed = [torch.cuda.Event() for _ in range(NB)]
+    d2h_done = [torch.cuda.Event() for _ in range(NB)]
+    keep = [None] * NB
     copy_ev = []
 
     def e2e_run(n_steps, record):
         for s_ in range(n_steps + 1):
             if s_ < n_steps:                      # stage batch s_ on the copy stream
-                b = s_ & 1
+                b = s_ % NB
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(consumed[b])
                     if record:
@@ -377,27 +381,32 @@ def e2e_measure(ctx, model, hx, B, H, W, steps):
                         copy_ev.append(("h2d", a0, a1))
                     ready[b].record(copy_stream)
             if s_ >= 1:                           # segment batch s_-1 on the main stream
-                b = (s_ - 1) & 1
+                b = (s_ - 1) % NB
                 main_stream.wait_event(ready[b])
-                main_stream.wait_event(d2h_done[b])      # labels of batch s_-3 are on the host:
+                main_stream.wait_event(d2h_done[b])      # labels of batch s_-1-NB are on the host:
                 keep[b] = labels = model.predict(xd[b])  # their device buffer may be recycled
+                if eval_mode is not None:
+                    eval_mode[0].update(labels, eval_mode[1])
                 consumed[b].record(main_stream)
                 with torch.cuda.stream(d2h_stream):      # labels go back on their own stream so the
                     d2h_stream.wait_event(consumed[b])   # next batch's kernels are not queued behind PCIe
                     if record:
                         a0 = torch.cuda.Event(enable_timing=True)
                         a0.record(d2h_stream)
-                    hl[b].copy_(labels, non_blocking=True)
+                    if eval_mode is not None:
+                        hh[b].copy_(eval_mode[0].hist, non_blocking=True)
+                    else:
+                        hl[b].copy_(labels, non_blocking=True)
                     if record:
                         a1 = torch.cuda.Event(enable_timing=True)
                         a1.record(d2h_stream)
                         copy_ev.append(("d2h", a0, a1))
                     d2h_done[b].record(d2h_stream)
 
-    for b in range(2):
+    for b in range(NB):
         consumed[b].record(main_stream)
         d2h_done[b].record(main_stream)
-    e2e_run(2, False)
+    e2e_run(NB, False)
     ctx.barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -411,33 +420,49 @@ def e2e_measure(ctx, model, hx, B, H, W, steps):
     h2d = [a.elapsed_time(b) for k, a, b in copy_ev if k == "h2d"]
     d2h = [a.elapsed_time(b) for k, a, b in copy_ev if k == "d2h"]
     h2d_gbs = hx.numel() * hx.element_size() / (sum(h2d) / len(h2d) * 1e-3) / 1e9
-    d2h_gbs = B * H * W / (sum(d2h) / len(d2h) * 1e-3) / 1e9
+    d2h_gbs = (19 * 19 * 8 if eval_mode is not None else B * H * W) / (sum(d2h) / len(d2h) * 1e-3) / 1e9
     return ms, h2d_gbs, d2h_gbs
 
 
-def host_ceiling(ctx, hx, seconds=0.4):
-    """H2D rate with ALL ranks copying their frame batch at once and NO kernel running: what the host (PCIe roots,
-    IOMMU, memory system) can feed to N GPUs.  e2e frames/s cannot exceed N x rate / bytes per frame."""
+def host_ceiling(ctx, hx, label_bytes, seconds=0.4):
+    """Copy rates with ALL ranks copying at once and NO kernel running: every rank moves its frame batch host->device
+    and a label-map-sized buffer device->host concurrently, as the e2e pipeline does.  What the host (PCIe roots, IOMMU,
+    memory system of the VM) can feed to N GPUs.  Ranks have equal work and the step time is the max over ranks, so
+    e2e frames/s cannot exceed N x (slowest rank's H2D rate) / bytes per frame.  -> (h2d GB/s, d2h GB/s) of this rank"""
     dev = ctx.dev
     dst = torch.empty(hx.shape, dtype=hx.dtype, device=dev)
+    lab = torch.empty(label_bytes, dtype=torch.uint8, device=dev)
+    hlab = torch.empty(label_bytes, dtype=torch.uint8).pin_memory()
+    back = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
     nbytes = hx.numel() * hx.element_size()
-    for _ in range(2):
+
+    def one():
         dst.copy_(hx, non_blocking=True)
+        with torch.cuda.stream(back):
+            hlab.copy_(lab, non_blocking=True)
+
+    for _ in range(2):
+        one()
     ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    dst.copy_(hx, non_blocking=True)
+    one()
     e1.record()
     torch.cuda.synchronize()
     reps = max(3, int(seconds * 1e3 / max(e0.elapsed_time(e1), 1e-3)))
     reps = int(ctx.max_over_ranks([reps])[0])
     ctx.barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    b0.record(back)
     for _ in range(reps):
-        dst.copy_(hx, non_blocking=True)
+        one()
     e1.record()
+    b1.record(back)
+    main.wait_stream(back)
     ctx.barrier()
-    return reps * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    return (reps * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9, reps * label_bytes / (b0.elapsed_time(b1) * 1e-3) / 1e9)
 
 
 def layer_table(eng, per_layer, B, H, W, pk):
@@ -446,7 +471,7 @@ def layer_table(eng, per_layer, B, H, W, pk):
     import drnb200
     lib = drnb200.ffi.lib()
     KERNELS = {0: "conv_tc<T>", 1: "conv_tc<P>", 2: "conv_tc<T,f32>", 3: "conv_gather", 4: "conv_halo",
-               5: "conv_tc<T,ROW>", -1: "conv_direct"}
+               5: "conv_tc<T,ROW>", 6: "conv_tc<T,ROW,PIX>", -1: "conv_direct"}
     layers = []
     shapes = {-1: (H, W)}
     ops = eng.last_ops or eng.ops
@@ -553,20 +578,23 @@ def main():
         hbuf = HostBuffer((B, 3, H, W), torch.float32, args.host_mode)
         hbuf.tensor.copy_(x.cpu())
         e2e_ms, h2d_gbs, d2h_gbs = e2e_measure(ctx, model, hbuf.tensor, B, H, W, args.steps)
-        ceiling = host_ceiling(ctx, hbuf.tensor) if extras else None
+        ceiling, ceiling_d2h = host_ceiling(ctx, hbuf.tensor, B * H * W) if extras else (None, None)
         # the same through the fused frame ingest: uint8 HWC frames as cv2 delivers them, the
         # reference's ToTensor + Normalize (info.json statistics) applied inside the stem kernel
-        e2e_u8_ms = u8_h2d = u8_d2h = None
+        e2e_u8_ms = u8_h2d = u8_d2h = e2e_ev_ms = ev_h2d = None
         if W % 16 == 0:
             model.set_ingest(INFO_MEAN, INFO_STD)
             hu8 = HostBuffer((B, H, W, 3), torch.uint8, args.host_mode)
             hu8.tensor.copy_(synthetic.make_u8_frames(B, H, W, seed=1234 + rank))
             e2e_u8_ms, u8_h2d, u8_d2h = e2e_measure(ctx, model, hu8.tensor, B, H, W, args.steps)
+            if extras:
+                e2e_ev_ms, ev_h2d, _ = e2e_measure(ctx, model, hu8.tensor, B, H, W, args.steps, eval_mode=(meter, gt))
             hu8.close()
         clocks = sampler.finish()
-        e2e_ms, e2e_u8_ms = ctx.max_over_ranks([e2e_ms, e2e_u8_ms or 0.0])
+        e2e_ms, e2e_u8_ms, e2e_ev_ms = ctx.max_over_ranks([e2e_ms, e2e_u8_ms or 0.0, e2e_ev_ms or 0.0])
         copy_rates = {k: ctx.gather(v) for k, v in (("h2d", h2d_gbs), ("d2h", d2h_gbs), ("u8_h2d", u8_h2d or 0.0),
-                                                    ("u8_d2h", u8_d2h or 0.0), ("ceiling", ceiling or 0.0))}
+                                                    ("u8_d2h", u8_d2h or 0.0), ("ev_h2d", ev_h2d or 0.0),
+                                                    ("ceiling", ceiling or 0.0), ("ceiling_d2h", ceiling_d2h or 0.0))}
         hbuf.close()
 
         # ---- per-layer timing pass (CUDA events per launch) for the roofline objects
@@ -606,10 +634,11 @@ def main():
         # the dominant kernel = the one with the largest share of the step (conv_tc_kernel<MODE_T, ROW>: the 3x3
         # stride-1 convs of layers 4-8), aggregated over its launches of one step
         by_kernel = collections.defaultdict(float)
+        fam = lambda name: name.replace(",PIX", "")     # noqa: E731  (both accumulator layouts of the row-halo kernel)
         for l in layers:
-            by_kernel[l["kernel"]] += l["ms"]
+            by_kernel[fam(l["kernel"])] += l["ms"]
         dom_name = max(by_kernel, key=by_kernel.get)
-        dom = [l for l in layers if l["kernel"] == dom_name]
+        dom = [l for l in layers if fam(l["kernel"]) == dom_name]
         dom_ms = sum(l["ms"] for l in dom)
         dom_tflops = 2.0 * sum(l["live_gmac"] for l in dom) * 1e9 / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
         dom_floor = sum(l["floor_ms"] for l in dom)
@@ -647,8 +676,9 @@ def main():
             "host_numa": ctx.numa,
             "clocks": clocks,
             "roofline": {"bound": "tensor",
-                         "kernel": "%s (%d launches per step: %s)" % (
-                             dom_name, len(dom), ", ".join(l["layer"].replace("layer.", "") for l in dom)),
+                         "kernel": "%s (%d launches per step: %s; * = pixel-major accumulator flavour)" % (
+                             dom_name, len(dom), ", ".join(l["layer"].replace("layer.", "") + ("*" if "PIX" in l["kernel"] else "")
+                                                           for l in dom)),
                          "achieved": dom_tflops, "peak": pk["tflops_burst"], "unit": "TFLOP/s",
                          "frac": dom_tflops / pk["tflops_burst"],
                          "frac_of_sustained_peak": dom_tflops / pk["tflops_sustained"],
@@ -680,17 +710,28 @@ def main():
             "miou_vs_random_labels": miou,
             "reduced_histogram_pixels": "asserted == world x steps x batch x H x W in every timed region",
         }
+        if e2e_ev_ms:
+            line["e2e_uint8_eval_mode"] = {
+                "value": frames / (e2e_ev_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes_u8,
+                "d2h_bytes_per_step": 19 * 19 * 8, "h2d_gbs_per_rank": [round(v, 2) for v in copy_rates["ev_h2d"]],
+                "note": "evaluation flow of semantic_seg.py test(): uint8 frames in, confusion matrix updated on the device, "
+                        "the 19x19 int64 matrix read back every step instead of the label map"}
         if ceil_rates:
-            agg = sum(ceil_rates)
+            slow = min(ceil_rates)
+            dev_rate = frames / (ms * 1e-3)
+            b_f32 = min(world * slow * 1e9 / frame_bytes_f32, dev_rate)
+            b_u8 = min(world * slow * 1e9 / frame_bytes_u8, dev_rate)
             line["host_ceiling"] = {
-                "what": "H2D GB/s with all %d ranks copying their frame batch at once, no kernels" % world,
-                "h2d_gbs_per_rank": [round(v, 2) for v in ceil_rates], "h2d_gbs_sum": round(agg, 1),
-                "e2e_frames_per_s_bound_f32_frames": agg * 1e9 / frame_bytes_f32,
-                "e2e_frames_per_s_bound_uint8_frames": agg * 1e9 / frame_bytes_u8,
-                "e2e_over_min(bound, device rate)": (frames / (e2e_ms * 1e-3)) / min(agg * 1e9 / frame_bytes_f32,
-                                                                                   frames / (ms * 1e-3)),
-                "e2e_uint8_over_min(bound, device rate)": None if not e2e_u8_ms else (
-                    (frames / (e2e_u8_ms * 1e-3)) / min(agg * 1e9 / frame_bytes_u8, frames / (ms * 1e-3)))}
+                "what": "copy rates with all %d ranks moving a frame batch H2D and a label map D2H at once, no kernels; ranks "
+                        "have equal work and a step ends with the slowest rank, so e2e <= N x slowest H2D rate / bytes "
+                        "per frame (and <= the device-timed rate)" % world,
+                "h2d_gbs_per_rank": [round(v, 2) for v in ceil_rates], "h2d_gbs_sum": round(sum(ceil_rates), 1),
+                "h2d_gbs_slowest_rank": round(slow, 2),
+                "d2h_gbs_per_rank": [round(v, 2) for v in copy_rates["ceiling_d2h"]],
+                "e2e_bound_f32_frames": b_f32, "e2e_bound_uint8_frames": b_u8,
+                "e2e_over_bound": (frames / (e2e_ms * 1e-3)) / b_f32,
+                "e2e_uint8_over_bound": None if not e2e_u8_ms else (frames / (e2e_u8_ms * 1e-3)) / b_u8,
+                "e2e_uint8_eval_mode_over_bound": None if not e2e_ev_ms else (frames / (e2e_ev_ms * 1e-3)) / b_u8}
         if sustained:
             line["sustained"] = sustained
         if other:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRNB200_VERSION 106
+#define DRNB200_VERSION 107
 
 /* error codes */
 #define DRNB200_OK          0
@@ -116,6 +116,11 @@ typedef struct drnb200_conv_desc {
    * than 128 pixels); plan creation fails with DRNB200_E_ARG otherwise and the caller keeps the projection as a
    * separate launch. */
   int32_t proj_cin;
+  /* Accumulator orientation of the row-halo kernel (mode 5/6 below): 0 = chosen from the tile list (pixel-major when
+   * an output tile has <= 12 live K-blocks on average, i.e. when finishing a tile costs more than multiplying it),
+   * 1 = cout-major (TMEM lane = cout, staged shared-memory epilogue with TMA stores), 2 = pixel-major (TMEM lane =
+   * pixel, register epilogue with 32-byte global accesses).  Results are identical; ignored by the other kernels. */
+  int32_t acc_layout;
 } drnb200_conv_desc;
 
 #define DRNB200_KB_PROJ (3 << 20)
@@ -133,7 +138,7 @@ int  drnb200_conv_plan_impl(const drnb200_conv_plan* plan);
  * 1 = conv_tc MODE_P (pixels as M), 2 = conv_tc MODE_T with float32 output, 3 = conv_gather (im2col in smem),
  * 4 = conv_halo (shifted windows of one halo tile), 5 = conv_tc MODE_T ROW variant (3x3 stride 1, 64-channel K-blocks,
  * rows wider than 128 pixels: each input row loaded once, the three kx taps as shifted UMMA windows; the only kernel
- * that accepts proj_cin); -1 for direct plans */
+ * that accepts proj_cin), 6 = the same with the pixel-major accumulator (acc_layout); -1 for direct plans */
 int  drnb200_conv_plan_mode(const drnb200_conv_plan* plan);
 /* live multiply-accumulates of one forward (tile-list granularity) — the numerator of tensor-pipe
  * utilisation counted at block granularity; element-granularity MACs are computed by the host. */

@@ -123,7 +123,8 @@ def test_weight_packing_bit_exact(act, tiles):
 
 
 # ------------------------------------------------------------------------------------------------ (b)
-def _conv_case(N, H, W, cin, cout, k, stride, dil, relu, res, act, impl, density, seed):
+def _conv_case(N, H, W, cin, cout, k, stride, dil, relu, res, act, impl, density, seed, out_f32=True, acc_layout=0,
+               expect_mode=None):
     """one conv+BN(+res)(+ReLU) through the C ABI vs torch fp32 on the same 16-bit-representable operands"""
     lib = ffi.lib()
     g = torch.Generator().manual_seed(seed)
@@ -161,20 +162,29 @@ def _conv_case(N, H, W, cin, cout, k, stride, dil, relu, res, act, impl, density
     ffi.check(lib.drnb200_pack_weights(ffi.ptr(wd), ffi.ptr(md), cout, cin, k, k, tile_o, tile_ci, ffi.ptr(rp),
                                        ffi.ptr(kb), act, ffi.ptr(packed), st))
     desc = ffi.ConvDesc(N=N, H=H, W=W, Cin=cin, Cout=cout, ksize=k, stride=stride, dilation=dil, relu=int(relu),
-                        has_residual=int(res), act_dtype=act, out_f32=1, tile_o=tile_o, tile_ci=tile_ci, impl=impl)
+                        has_residual=int(res), act_dtype=act, out_f32=int(out_f32), tile_o=tile_o, tile_ci=tile_ci,
+                        impl=impl, acc_layout=acc_layout)
     plan = C.c_void_p()
     sc, sh = scale.to(d), shift.to(d)
     ffi.check(lib.drnb200_conv_plan_create(C.byref(plan), C.byref(desc), ffi.ptr(rp), ffi.ptr(kb), ffi.ptr(packed),
                                            ffi.ptr(sc), ffi.ptr(sh)))
     assert lib.drnb200_conv_plan_impl(plan) == impl
-    y = torch.full((N, OH, OW, cout), float("nan"), dtype=torch.float32, device=d)
+    if expect_mode is not None:
+        assert lib.drnb200_conv_plan_mode(plan) == expect_mode
+    # guard bands around the output: the kernels write nothing outside their tensor
+    G = 4096
+    flat = torch.full((N * OH * OW * cout + 2 * G,), float("nan"), dtype=torch.float32 if out_f32 else tdt, device=d)
+    y = flat[G:G + N * OH * OW * cout].view(N, OH, OW, cout)
     ffi.check(lib.drnb200_conv_forward(plan, ffi.ptr(xd), ffi.ptr(rd), ffi.ptr(y), st))
     torch.cuda.synchronize()
     lib.drnb200_conv_plan_destroy(plan)
-    got = y.permute(0, 3, 1, 2).cpu()
+    assert bool(torch.isnan(flat[:G]).all()) and bool(torch.isnan(flat[-G:]).all())
+    got = y.float().permute(0, 3, 1, 2).cpu()
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item()
-    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
+    tol = 2e-3 if out_f32 else (2.0 ** -8 if act == ffi.BF16 else 2.0 ** -10)      # 16-bit output: one rounding
+    assert err <= tol * max(1.0, ref.abs().max().item()), "max abs err %g" % err
+    return got
 
 
 CONV_CASES = [
@@ -200,6 +210,31 @@ def test_conv_tcgen05_vs_fp32(case, act):
     _conv_case(N, H, W, cin, cout, k, s, d, relu, res, act, ffi.IMPL_TCGEN05, dens, seed=hash(case) & 0xFFFF)
 
 
+ROW_CASES = [
+    # N  H   W   cin cout d  relu  res   density      3x3 stride-1 convs over 64-channel K-blocks, rows of > 128 pixels
+    (1, 5, 300, 128, 256, 2, True, True, 0.5),        # ragged second row tile (300 = 256 + 44), dilation 2, residual
+    (2, 3, 257, 64, 128, 1, True, False, 1.0),        # one pixel in the second tile
+    (1, 2, 512, 256, 256, 4, True, True, 0.25),       # dilation 4, 75 % sparse, two full tiles
+    (1, 3, 256, 128, 512, 1, False, True, 0.5),       # no ReLU, four cout tiles
+    (1, 2, 264, 128, 128, 2, True, False, 0.0),       # everything pruned: y = relu(shift)
+]
+
+
+@pytest.mark.parametrize("case", ROW_CASES)
+@pytest.mark.parametrize("layout", [1, 2])
+@pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
+def test_conv_row_kernel_both_accumulator_layouts(case, layout, act):
+    """the row-halo kernel with the cout-major accumulator + staged epilogue (mode 5) and with the pixel-major
+    accumulator + register epilogue (mode 6, drnb200_conv_desc.acc_layout) against torch fp32, and against each other:
+    both accumulate the same products in fp32 and round once, so their outputs must be bit-identical"""
+    N, H, W, cin, cout, dil, relu, res, dens = case
+    outs = []
+    for lay in (layout, 3 - layout):
+        outs.append(_conv_case(N, H, W, cin, cout, 3, 1, dil, relu, res, act, ffi.IMPL_TCGEN05, dens,
+                               seed=W + cin + cout, out_f32=False, acc_layout=lay, expect_mode=4 + lay))
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("case", CONV_CASES[:9])
 def test_conv_direct_vs_fp32(case):
     N, H, W, cin, cout, k, s, d, relu, res, dens = case
@@ -207,9 +242,10 @@ def test_conv_direct_vs_fp32(case):
 
 
 @pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
+@pytest.mark.parametrize("layout", [1, 2])
 @pytest.mark.parametrize("geom", [(1, 5, 300, 128, 256, 64, 64, 0, 2), (2, 3, 257, 64, 128, 128, 192, 64, 4),
                                   (1, 2, 512, 256, 256, 128, 128, 0, 1)])
-def test_conv_projection_k_blocks_vs_fp32(geom, act):
+def test_conv_projection_k_blocks_vs_fp32(geom, layout, act):
     """drnb200_conv_desc.proj_cin through the C ABI: 3x3 conv over h plus 1x1 projection of a second tensor x inside
     the same K loop (DRNB200_KB_PROJ entries), ragged row tiles, tiles with only-conv / only-projection / no entries,
     projection input as a channel sub-range; vs torch fp32 on the same 16-bit-representable operands"""
@@ -265,12 +301,12 @@ def test_conv_projection_k_blocks_vs_fp32(geom, act):
     rp = torch.tensor(row_ptr, dtype=torch.int32, device=d)
     desc = ffi.ConvDesc(N=N, H=H, W=W, Cin=cin, Cout=cout, ksize=3, stride=1, dilation=dil, relu=1, has_residual=0,
                         act_dtype=act, out_f32=0, tile_o=128, tile_ci=64, impl=ffi.IMPL_TCGEN05, res_cpitch=ppitch,
-                        res_coffset=poff, proj_cin=pcin)
+                        res_coffset=poff, proj_cin=pcin, acc_layout=layout)
     plan = C.c_void_p()
     sc, sh = scale.to(d), shift.to(d)
     ffi.check(lib.drnb200_conv_plan_create(C.byref(plan), C.byref(desc), ffi.ptr(rp), ffi.ptr(kblk), ffi.ptr(packed),
                                            ffi.ptr(sc), ffi.ptr(sh)))
-    assert lib.drnb200_conv_plan_mode(plan) == 5                       # row-halo kernel
+    assert lib.drnb200_conv_plan_mode(plan) == 4 + layout              # row-halo kernel, either accumulator layout
     hd = h.permute(0, 2, 3, 1).contiguous().to(d)
     xd = xfull.permute(0, 2, 3, 1).contiguous().to(d)
     y = torch.full((N, H, W, cout), float("nan"), dtype=tdt, device=d)
@@ -450,7 +486,16 @@ def test_parity_gates_at_benchmark_size():
     lab, ref_lab = _gates("config 2 D-22 BlockPruner 75% 1024x2048 (benchmark size)", model, sd, x)
     eng = model.engine()
     modes = [ffi.lib().drnb200_conv_plan_mode(p) for op in eng.last_ops for p in op.plans.values()]
-    assert eng.last_ops is eng.ops_proj and modes.count(5) == 13        # the launch list bench.py measures
+    assert eng.last_ops is eng.ops_proj and modes.count(5) + modes.count(6) == 13     # the launch list bench.py measures
+    # forcing either accumulator layout everywhere gives the same labels bit for bit
+    from drnb200.engine import ConvLayer
+    base = model.predict(x.to(dev()))
+    try:
+        for lay in (1, 2):
+            ConvLayer.acc_layout = lay
+            assert torch.equal(model.predict(x.to(dev())), base), lay
+    finally:
+        ConvLayer.acc_layout = 0
     # uint8 labels straight from the fused head equal the int64 labels of torch.max on the host, frame by frame
     assert lab.shape == (2, 1024, 2048)
 
@@ -513,7 +558,7 @@ def test_parity_gates_wide_frames_projection_in_k(arch):
     for o in eng.last_ops:
         if isinstance(o, ProjResidualConv):
             kb = o.kblk.cpu().numpy()[:o.n_live]
-            assert (kb >= ffi.KB_PROJ).sum() > 0 and ffi.lib().drnb200_conv_plan_mode(list(o.plans.values())[0]) == 5
+            assert (kb >= ffi.KB_PROJ).sum() > 0 and ffi.lib().drnb200_conv_plan_mode(list(o.plans.values())[0]) in (5, 6)
     # the two launch lists give the same labels up to the re-rounded projection weights
     eng.proj_in_k = False
     lab_b = model.predict(x.to(dev()))

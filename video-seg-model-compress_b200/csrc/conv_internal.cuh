@@ -35,6 +35,7 @@ struct ConvParams {
   int ep_cw, ep_ch, ep_nch;   // chunk box (pixels wide x high), chunks per tile
   // ---- ROW variant of MODE_T (conv_tc.cu): input-row halo ring + weight-tile ring
   int row_mode, x_ring, w_ring, dbg;
+  int pix_mode;               // ROW variant with the pixel-major accumulator (operands swapped, register epilogue)
   int ep_groups;              // MODE_T: epilogue groups of four warps (2 or 4)
   uint32_t main_bytes;
 };

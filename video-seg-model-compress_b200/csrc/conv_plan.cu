@@ -24,6 +24,7 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
               d.tile_o, d.tile_ci);
   DRN_REQUIRE(d.impl >= DRNB200_IMPL_AUTO && d.impl <= DRNB200_IMPL_TCGEN05,
               "conv_plan_create: bad impl %d", d.impl);
+  DRN_REQUIRE(d.acc_layout >= 0 && d.acc_layout <= 2, "conv_plan_create: bad acc_layout %d", d.acc_layout);
 
   drnb200_conv_plan* plan = new (std::nothrow) drnb200_conv_plan();
   if (!plan) { set_error("conv_plan_create: out of host memory"); return DRNB200_E_NOMEM; }
@@ -127,7 +128,7 @@ extern "C" int drnb200_conv_plan_impl(const drnb200_conv_plan* plan) { return pl
 
 extern "C" int drnb200_conv_plan_mode(const drnb200_conv_plan* plan) {
   if (!plan || plan->impl != DRNB200_IMPL_TCGEN05) return -1;
-  return (plan->tc_mode == 0 && plan->p.row_mode) ? 5 : plan->tc_mode;
+  return (plan->tc_mode == 0 && plan->p.row_mode) ? (plan->p.pix_mode ? 6 : 5) : plan->tc_mode;
 }
 
 extern "C" int64_t drnb200_conv_plan_tile_macs(const drnb200_conv_plan* plan) {

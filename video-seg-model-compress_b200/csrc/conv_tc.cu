@@ -30,6 +30,16 @@
 // operand is the UMMA descriptor started kx*dil pixel rows further (the UMMA swizzle uses absolute shared-memory
 // address bits, conv_halo.cu).  Activation traffic drops from 9 x 32 KB to 3 x 33 KB per 64-channel block; rows and
 // weight tiles travel through two independent rings (X: 33 KB slots, W: 16 KB slots).
+//
+// PIX flavour of the ROW variant (tiles with FEW live K-blocks: layers 4-5, 6.0.conv1 at 75 % block sparsity).  The
+// staged epilogue above costs ~7000 cycles per 256-pixel x 128-cout tile whatever the K length (TMEM lane = cout
+// forces a transpose through shared memory, a residual TMA load and a TMA store per 32-pixel chunk, five mbarrier
+// hand-offs per chunk), i.e. as much as 14 K-blocks of MMA.  With the operands swapped — A = the input-row window
+// (M = 128 pixels, two M-blocks per 256-pixel row), B = the 128 x 64 weight tile (N = 128 couts) — the SAME shared
+// memory images feed the tensor pipe at the same rate, but the accumulator arrives pixel-major (TMEM lane = pixel,
+// column = cout): a thread owns one pixel and finishes 16 consecutive couts at a time straight from registers
+// (BN affine from shared memory, residual by one 32-byte global load, one 32-byte global store): no staging ring,
+// no store warp, no transposition.
 #include "conv_internal.cuh"
 #include <algorithm>
 #include <cstdlib>
@@ -52,10 +62,11 @@ constexpr int kRowHaloPx = kRowPx + 8;            // + 2*dil (dil <= 4) halo pix
 constexpr int kRowBytes = kRowHaloPx * 128;       // one X-ring slot (33 x 1024 B)
 constexpr int kRowWBytes = 128 * 128;             // one W-ring slot: 128 couts x 64 ch x 2 B
 constexpr int kMaxXRing = 4;
+constexpr double kPixMaxLive = -1.0;              // auto never picks the PIX flavour: measured slower on every layer (see below)
 
 struct __align__(16) TcSync {
-  alignas(16) float scale[256];   // MODE_P: BN affine of all (<= 256) output channels, read by every pixel thread
-  alignas(16) float shift[256];   //         (no L1 is left once the CTA takes ~all shared memory)
+  alignas(16) float scale[512];   // MODE_P / PIX: BN affine of all (<= 512) output channels, read by every pixel thread
+  alignas(16) float shift[512];   //         (no L1 is left once the CTA takes ~all shared memory)
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t xfull[kMaxXRing];  // ROW variant: input-row ring (full/empty above are then the weight-tile ring)
@@ -98,12 +109,13 @@ __device__ __forceinline__ float finish(float acc, float sc, float sh, float res
 // NG = epilogue groups of four warps (MODE_T): 2 when the MMA loop dominates a tile, 4 for tiles with few live K-blocks
 // (fused downsample rows, 1x1 projections, heavily pruned layers), where finishing a 128 x 256 accumulator tile
 // (~7000 cycles with two groups: dependent 2-byte shared-memory accesses, ~6 cycles per instruction) is the bound.
-template <int MODE, int DT, bool ROW = false, int NG = 2>
+template <int MODE, int DT, bool ROW = false, int NG = 2, bool PIX = false>
 __global__ void __launch_bounds__(tc_threads(NG), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_y,
                const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_x2,
                const ConvParams p) {
   static_assert(!ROW || MODE == MODE_T, "the ROW mainloop feeds the staged MODE_T epilogue");
+  static_assert(!PIX || (ROW && NG == 2), "the pixel-major accumulator exists for the ROW mainloop with two epilogue groups");
   static_assert(NG == 2 || (MODE == MODE_T && NG == 4), "four epilogue groups exist for the staged epilogue only");
   constexpr int kEpRing = 2 * NG;             // = 2 * D below: D chunks being finished + D draining / being prepared
   extern __shared__ uint8_t smem_raw[];
@@ -148,8 +160,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     tmem_alloc(&sync->tmem_base, kTmemCols);
     tmem_relinquish();
   }
-  if (MODE == MODE_P) {
-    for (int ch = threadIdx.x; ch < 256; ch += tc_threads(NG)) {
+  if (MODE == MODE_P || PIX) {
+    for (int ch = threadIdx.x; ch < 512; ch += tc_threads(NG)) {
       sync->scale[ch] = ch < p.Cout ? __ldg(p.scale + ch) : 0.f;
       sync->shift[ch] = ch < p.Cout ? __ldg(p.shift + ch) : 0.f;
     }
@@ -261,9 +273,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             const uint32_t sW16 = w16 + ws * (uint32_t)(kRowWBytes >> 4);
             if (elect_one()) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                umma_f16(d_tmem, d_hi | (uint64_t)(sW16 + 2u * i), d_hi | (uint64_t)(sX16 + kx * shift16 + 2u * i),
-                         p.idesc, (j > c.jb || i > 0) ? 1u : 0u);
+              for (int i = 0; i < 4; ++i) {
+                const uint64_t dW = d_hi | (uint64_t)(sW16 + 2u * i), dX = d_hi | (uint64_t)(sX16 + kx * shift16 + 2u * i);
+                const uint32_t accum = (j > c.jb || i > 0) ? 1u : 0u;
+                if (!PIX) {
+                  umma_f16(d_tmem, dW, dX, p.idesc, accum);
+                } else {        // pixels as M: rows 0-127 and 128-255 of the window, 128 columns (couts) each
+                  umma_f16(d_tmem, dX, dW, p.idesc, accum);
+                  umma_f16(d_tmem + 128u, dX + (uint64_t)(128u * 128u >> 4), dW, p.idesc, accum);
+                }
+              }
               umma_commit(&sync->empty[ws]);
             }
             __syncwarp();
@@ -325,7 +344,80 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     uint16_t* y16 = reinterpret_cast<uint16_t*>(p.y);
     float* y32 = reinterpret_cast<float*>(p.y);
 
-    if (MODE == MODE_T) {
+    if (PIX) {
+      // ------------------------------------------------ pixel-major accumulator: registers -> global, no staging
+      // warps 2..9: group (warp-2)>>2 owns the M-block of pixels [128*grp, 128*grp+128) of the row tile, the warp its
+      // TMEM lane quarter; thread = one output pixel.  32 couts per step: the TMEM load and the two 32-byte residual
+      // loads of step s+1 are in flight while step s is finished (BN affine from shared memory as float4 broadcasts)
+      // and written with two 32-byte global stores.
+      if (warp < 2 + 4 * NG) {
+        const int grp = (warp - 2) >> 2;
+        const int px = grp * 128 + q * 32 + lane;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+          const TileCoord c = decode_tile(p, t);
+          const bool live = c.je > c.jb;
+          const int ox = c.ox0 + px;
+          const bool valid = ox < p.OW;                               // TH == 1: the row itself is always inside
+          const bool use_res = p.has_res && valid;
+          const size_t pix = ((size_t)c.n * p.OH + c.oy0) * p.OW + ox;
+          const uint16_t* rrow = res16 + pix * p.res_pitch + p.res_coff + c.ot * 128;
+          uint16_t* yrow = y16 + pix * p.Cout + c.ot * 128;
+          const float* sc = sync->scale + c.ot * 128;
+          const float* sh = sync->shift + c.ot * 128;
+          const float floor_v = (c.ot * 128 < p.relu_n) ? 0.f : -INFINITY;   // relu_n is a multiple of 128 (plan check)
+          uint32_t rw[2][16], v[2][32];
+          if (use_res) { ldg256_nc(rrow, *reinterpret_cast<uint32_t(*)[8]>(&rw[0][0])); ldg256_nc(rrow + 16, *reinterpret_cast<uint32_t(*)[8]>(&rw[0][8])); }
+          if (live) {
+            mbar_wait(&sync->tfull[acc], acc_phase);
+            tc_fence_after();
+          }
+          const uint32_t t_addr = tmem_base + acc * 256u + (uint32_t)(grp * 128) + ((uint32_t)(q * 32) << 16);
+          if (live) tmem_ld32(t_addr, v[0]);
+#pragma unroll
+          for (int st = 0; st < 4; ++st) {
+            const int cb = st * 32;
+            if (live) tmem_ld_wait();
+            if (st < 3) {
+              if (live) tmem_ld32(t_addr + (uint32_t)(cb + 32), v[(st + 1) & 1]);
+              if (use_res) {
+                ldg256_nc(rrow + cb + 32, *reinterpret_cast<uint32_t(*)[8]>(&rw[(st + 1) & 1][0]));
+                ldg256_nc(rrow + cb + 48, *reinterpret_cast<uint32_t(*)[8]>(&rw[(st + 1) & 1][8]));
+              }
+            } else if (live) {             // the accumulator has been read out: hand it back before finishing the step
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&sync->tempty[acc]);
+            }
+            uint32_t w[16];
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(sc + cb + 4 * i4);
+              const float4 h4 = *reinterpret_cast<const float4*>(sh + cb + 4 * i4);
+              const uint32_t r0 = rw[st & 1][2 * i4], r1 = rw[st & 1][2 * i4 + 1];
+              float a0 = live ? __uint_as_float(v[st & 1][4 * i4 + 0]) : 0.f, a1 = live ? __uint_as_float(v[st & 1][4 * i4 + 1]) : 0.f;
+              float a2 = live ? __uint_as_float(v[st & 1][4 * i4 + 2]) : 0.f, a3 = live ? __uint_as_float(v[st & 1][4 * i4 + 3]) : 0.f;
+              a0 = fmaf(a0, s4.x, h4.x); a1 = fmaf(a1, s4.y, h4.y); a2 = fmaf(a2, s4.z, h4.z); a3 = fmaf(a3, s4.w, h4.w);
+              if (p.has_res) {
+                a0 += use_res ? Act<DT>::to_f32((uint16_t)(r0 & 0xFFFFu)) : 0.f;
+                a1 += use_res ? Act<DT>::to_f32((uint16_t)(r0 >> 16)) : 0.f;
+                a2 += use_res ? Act<DT>::to_f32((uint16_t)(r1 & 0xFFFFu)) : 0.f;
+                a3 += use_res ? Act<DT>::to_f32((uint16_t)(r1 >> 16)) : 0.f;
+              }
+              w[2 * i4] = pack2<DT>(fmaxf(a0, floor_v), fmaxf(a1, floor_v));
+              w[2 * i4 + 1] = pack2<DT>(fmaxf(a2, floor_v), fmaxf(a3, floor_v));
+            }
+            if (valid) {
+              stg256(yrow + cb, *reinterpret_cast<uint32_t(*)[8]>(&w[0]));
+              stg256(yrow + cb + 16, *reinterpret_cast<uint32_t(*)[8]>(&w[8]));
+            }
+          }
+          if (live) {
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+          }
+        }
+      }
+    } else if (MODE == MODE_T) {
       // ------------------------------------------------ staged: smem transpose + TMA load/store
       // warps 2 .. 2+4*NG-1 = NG groups of four warps taking 32-pixel chunks round-robin (flat chunk index k: group
       // k % NG, ring slot k % (2*NG)); the last warp issues every residual load and output store and recycles the slots.
@@ -588,9 +680,9 @@ static int ilog2(int v) {
   return r;
 }
 
-template <int MODE, int DT, bool ROW = false, int NG = 2>
+template <int MODE, int DT, bool ROW = false, int NG = 2, bool PIX = false>
 static int set_attr(size_t smem) {
-  DRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, DT, ROW, NG>,
+  DRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE, DT, ROW, NG, PIX>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return DRNB200_OK;
 }
@@ -671,10 +763,23 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
     while ((size_t)xr * kRowBytes + (size_t)wr * kRowWBytes + fixed > kMaxSmem && wr > 2) --wr;
     p.row_mode = 1; p.x_ring = xr; p.w_ring = wr;
     p.main_bytes = (uint32_t)(xr * kRowBytes + wr * kRowWBytes);
+    // pixel-major accumulator for tiles with few live K-blocks (the staged epilogue costs ~14 K-blocks of MMA time
+    // per tile; measured cross-over below).  DRNB200_PIX=0/1 forces it off/on for A/B runs.
+    static const char* env_pix = getenv("DRNB200_PIX");
+    const double avg_live = (double)plan->h_row_ptr[p.n_ot] / std::max(1, p.n_ot);
+    const bool pix_ok = p.ep_groups == 2 && p.Cout <= 512 && p.relu_n % 128 == 0;
+    const int want = d.acc_layout == 2 || (env_pix && env_pix[0] == '1') ? 1
+                     : d.acc_layout == 1 || (env_pix && env_pix[0] == '0') ? 0 : (avg_live <= kPixMaxLive);
+    if (pix_ok && want) {
+      p.pix_mode = 1;
+      p.idesc = umma_idesc_f16(128, 128, d.act_dtype);
+    }
   }
   int rc;
   const bool bf16 = d.act_dtype == DRNB200_BF16;
-  if (mode == MODE_T && p.row_mode && p.ep_groups == 4)
+  if (mode == MODE_T && p.row_mode && p.pix_mode)
+    rc = bf16 ? set_attr<MODE_T, DRNB200_BF16, true, 2, true>(plan->smem_bytes) : set_attr<MODE_T, DRNB200_F16, true, 2, true>(plan->smem_bytes);
+  else if (mode == MODE_T && p.row_mode && p.ep_groups == 4)
     rc = bf16 ? set_attr<MODE_T, DRNB200_BF16, true, 4>(plan->smem_bytes) : set_attr<MODE_T, DRNB200_F16, true, 4>(plan->smem_bytes);
   else if (mode == MODE_T && p.row_mode)
     rc = bf16 ? set_attr<MODE_T, DRNB200_BF16, true>(plan->smem_bytes) : set_attr<MODE_T, DRNB200_F16, true>(plan->smem_bytes);
@@ -849,7 +954,11 @@ int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st) {
     if (bf) conv_tc_kernel<MODE_T, DRNB200_BF16, ROWV, NGV><<<grid, blk, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p); \
     else    conv_tc_kernel<MODE_T, DRNB200_F16, ROWV, NGV><<<grid, blk, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);  \
   } while (0)
-  if (plan->tc_mode == MODE_T && (p.row_mode || p.ep_groups == 4)) {
+  if (plan->tc_mode == MODE_T && p.row_mode && p.pix_mode) {
+    const dim3 blk(tc_threads(2));
+    if (bf) conv_tc_kernel<MODE_T, DRNB200_BF16, true, 2, true><<<grid, blk, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);
+    else    conv_tc_kernel<MODE_T, DRNB200_F16, true, 2, true><<<grid, blk, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);
+  } else if (plan->tc_mode == MODE_T && (p.row_mode || p.ep_groups == 4)) {
     if (p.row_mode && p.ep_groups == 4) DRN_LAUNCH_T(true, 4);
     else if (p.row_mode) DRN_LAUNCH_T(true, 2);
     else DRN_LAUNCH_T(false, 4);

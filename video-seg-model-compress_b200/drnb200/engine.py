@@ -51,6 +51,8 @@ def _effective_weight(conv):
 class ConvLayer:
     """one conv (+BN) (+residual) (+ReLU) of the network and its derived device-side cache"""
 
+    acc_layout = 0      # drnb200_conv_desc.acc_layout for new plans: 0 auto, 1 cout-major, 2 pixel-major (A/B runs, tests)
+
     def __init__(self, key, conv, bn, relu, residual_from=None, input_from=None):
         self.key = key                  # state_dict key prefix of the conv, e.g. 'layer.3.0.conv1'
         self.conv, self.bn, self.relu = conv, bn, relu
@@ -168,7 +170,7 @@ class ConvLayer:
         return True
 
     def plan(self, N, H, W, act_dtype, impl):
-        k = (N, H, W, act_dtype, impl, self.out_f32)
+        k = (N, H, W, act_dtype, impl, self.out_f32, ConvLayer.acc_layout)
         p = self.plans.get(k)
         if p is None:
             conv = self.conv
@@ -177,7 +179,8 @@ class ConvLayer:
                              relu=int(self.relu), has_residual=int(self.residual_from is not None),
                              act_dtype=act_dtype, out_f32=int(self.out_f32), tile_o=self.tile_o,
                              tile_ci=self.tile_ci, impl=impl, x_cpitch=self.x_cpitch,
-                             res_cpitch=self.res_cpitch, res_coffset=self.res_coffset, relu_n=self.relu_n)
+                             res_cpitch=self.res_cpitch, res_coffset=self.res_coffset, relu_n=self.relu_n,
+                             acc_layout=ConvLayer.acc_layout)
             h = C.c_void_p()
             ffi.check(ffi.lib().drnb200_conv_plan_create(
                 C.byref(h), C.byref(d), ffi.ptr(self.row_ptr), ffi.ptr(self.kblk), ffi.ptr(self.w_packed),
@@ -347,14 +350,15 @@ class ProjResidualConv(ConvLayer):
         return True
 
     def plan(self, N, H, W, act_dtype, impl):
-        k = (N, H, W, act_dtype, impl)
+        k = (N, H, W, act_dtype, impl, ConvLayer.acc_layout)
         p = self.plans.get(k)
         if p is None:
             conv = self.conv
             d = ffi.ConvDesc(N=N, H=H, W=W, Cin=conv.in_channels, Cout=conv.out_channels, ksize=3, stride=1,
                              dilation=conv.dilation[0], relu=1, has_residual=0, act_dtype=act_dtype, out_f32=0,
                              tile_o=128, tile_ci=64, impl=ffi.IMPL_TCGEN05, x_cpitch=self.x_cpitch,
-                             res_cpitch=self.res_cpitch, res_coffset=0, relu_n=0, proj_cin=self.proj_cin)
+                             res_cpitch=self.res_cpitch, res_coffset=0, relu_n=0, proj_cin=self.proj_cin,
+                             acc_layout=ConvLayer.acc_layout)
             h = C.c_void_p()
             ffi.check(ffi.lib().drnb200_conv_plan_create(
                 C.byref(h), C.byref(d), ffi.ptr(self.row_ptr), ffi.ptr(self.kblk), ffi.ptr(self.w_packed),

@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "ksize", "stride", "dilation", "relu", "has_residual",
         "act_dtype", "out_f32", "tile_o", "tile_ci", "impl", "x_cpitch", "res_cpitch", "res_coffset", "relu_n",
-        "proj_cin")]
+        "proj_cin", "acc_layout")]
 
 
 # name -> (restype, argtypes); every symbol include/drnb200.h declares
