@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRNB200_VERSION 107
+#define DRNB200_VERSION 108
 
 /* error codes */
 #define DRNB200_OK          0
@@ -205,6 +205,13 @@ void drnb200_head_plan_destroy(drnb200_head_plan* plan);
  * C <= 1024, classes <= 19); otherwise, and whenever logits or log-probs are requested, the classifier GEMM and
  * the upsample run as two launches over a float32 [N,h,w,32] scratch. */
 int  drnb200_head_plan_fused(const drnb200_head_plan* plan);
+/* Which `up` module the plan reproduces (semantic_seg.py:144-152):
+ *   DRNB200_UP_TRANSPOSED  the fixed-bilinear grouped ConvTranspose2d(k16,s8,p4) (default, the reference's default);
+ *   DRNB200_UP_ALIGNED     nn.UpsamplingBilinear2d(scale_factor=8) of `use_torch_up=True`: bilinear interpolation with
+ *                          align_corners=True.  Always the two-launch form (drnb200_head_plan_fused returns 0). */
+#define DRNB200_UP_TRANSPOSED 0
+#define DRNB200_UP_ALIGNED    1
+int  drnb200_head_plan_set_upsample(drnb200_head_plan* plan, int mode);
 
 /* Confusion matrix accumulation: fast_hist (semantic_seg.py:293-296).
  * hist[label*classes + pred] += 1 for every pixel with 0 <= label < classes (255 = ignore falls out).

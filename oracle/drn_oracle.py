@@ -133,10 +133,14 @@ def up_weights(k=16):
     return torch.tensor([1 - abs(i / f - c) for i in range(k)], dtype=torch.float64)
 
 
-def head_forward(sd, feat, up_weight=None):
-    """seg 1x1 -> grouped ConvTranspose2d(k16,s8,p4) -> LogSoftmax(dim=1)   (semantic_seg.py:154-158)"""
+def head_forward(sd, feat, up_weight=None, use_torch_up=False):
+    """seg 1x1 -> grouped ConvTranspose2d(k16,s8,p4) -> LogSoftmax(dim=1)   (semantic_seg.py:154-158);
+    `use_torch_up`: nn.UpsamplingBilinear2d(scale_factor=8) instead (semantic_seg.py:144-145)"""
     seg = F.conv2d(feat, sd["seg.weight"], sd["seg.bias"])
     classes = seg.shape[1]
+    if use_torch_up:
+        y = F.interpolate(seg, scale_factor=8, mode="bilinear", align_corners=True)
+        return F.log_softmax(y, dim=1), seg
     if up_weight is None:
         up_weight = sd.get("up.weight")
     if up_weight is None:
@@ -147,13 +151,13 @@ def head_forward(sd, feat, up_weight=None):
 
 
 @torch.no_grad()
-def drnseg_forward(sd, x, prefix=None, taps=None, raw=None, quant=None):
+def drnseg_forward(sd, x, prefix=None, taps=None, raw=None, quant=None, use_torch_up=False):
     """DRNSeg.forward(x) -> (logprob [N,C,H,W], seg_logits [N,C,H/8,W/8])  fp32 on CPU"""
     sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items() if torch.is_floating_point(v)}
     if prefix is None:
         prefix = "layer" if any(k.startswith("layer.") for k in sd) else "base"
     feat = backbone_forward(sd, x.detach().to("cpu", torch.float32), prefix, taps, raw, quant)
-    return head_forward(sd, feat)
+    return head_forward(sd, feat, use_torch_up=use_torch_up)
 
 
 def predict_labels(sd, x, prefix=None):

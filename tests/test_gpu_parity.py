@@ -780,6 +780,34 @@ def test_head_borders_against_conv_transpose():
     assert int(lab.max()) == 0
 
 
+def test_use_torch_up_against_the_real_reference():
+    """DRNSeg(use_torch_up=True): nn.UpsamplingBilinear2d(scale_factor=8) (align_corners=True) instead of the fixed
+    ConvTranspose2d (semantic_seg.py:144-145).  Fixture produced by the real reference; no `up.weight` key exists."""
+    fx = np.load(golden("fwd_drn_d_22_40x72_torch_up.npz"))
+    shapes = collections.OrderedDict((k, v) for k, v in load_keys("drn_d_22").items() if k != "up.weight")
+    sd = recipe.make_state_dict(shapes, seed=int(fx["seed"]))
+    model = drnb200.DRNSeg("drn_d_22", 19, pretrained=False, use_torch_up=True)
+    assert "up.weight" not in model.state_dict()
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model = model.to(dev()).eval()
+    x = recipe.make_frames(1, int(fx["hw"][0]), int(fx["hw"][1]), seed=1234 + int(fx["seed"])).to(dev())
+    with torch.no_grad():
+        lp, seg = model(x)
+        lab = model.predict(x)
+    assert not ffi.lib().drnb200_head_plan_fused(list(model.engine().head_plans.values())[0])
+    assert torch.equal(torch.max(lp, 1)[1].to(torch.uint8), lab)
+    rng = np.abs(fx["seg"]).max()
+    e_seg = float(np.abs(seg.cpu().numpy() - fx["seg"]).max() / rng)
+    e_lp = float(np.abs(lp.cpu().numpy() - fx["logprob"]).max() / rng)
+    differ = int((lab.cpu().numpy() != fx["labels"]).sum())
+    record("real-reference fixture use_torch_up=True drn_d_22 40x72", act="fp16", frames="1x40x72",
+           label_agreement=1.0 - differ / fx["labels"].size, pixels_differ=differ, pixels=int(fx["labels"].size),
+           logits_rel_err=e_seg, logprob_rel_err=e_lp)
+    assert e_seg <= LOGIT_RTOL and e_lp <= LOGIT_RTOL
+    assert differ <= max(2, int(fx["labels"].size * (1 - LABEL_AGREE)))
+
+
 def test_confusion_matrix_and_ignore_label():
     fx = np.load(golden("metrics.npz"))
     pred = torch.from_numpy(fx["pred"].astype(np.uint8)).to(dev())

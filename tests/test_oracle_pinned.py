@@ -4,8 +4,10 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import fixture_frames, fixture_state_dict, golden
-from oracle import compact_oracle, drn_oracle
+import collections
+
+from helpers import fixture_frames, fixture_state_dict, golden, load_keys
+from oracle import compact_oracle, drn_oracle, recipe
 
 FWD = [("fwd_drn_d_22_64x128_dense.npz", "drn_d_22"), ("fwd_drn_d_22_64x128_block75.npz", "drn_d_22"),
        ("fwd_drn_d_38_32x64_block75.npz", "drn_d_38"), ("fwd_drn_d_54_32x64_dense.npz", "drn_d_54"),
@@ -144,3 +146,15 @@ def test_multiscale_resize_sum_argmax_match_reference():
     assert kk.shape[1] == 3 and np.allclose(kk.sum(1), 1.0) and cnt.max() <= 3
     xmin, cnt, kk = ms_oracle.bilinear_coeffs(98, 56)
     assert kk.shape[1] == 5 and cnt.max() <= 5
+
+
+def test_oracle_use_torch_up_matches_the_real_reference():
+    """use_torch_up=True (nn.UpsamplingBilinear2d, semantic_seg.py:144-145): oracle vs the real reference's output"""
+    fx = np.load(golden("fwd_drn_d_22_40x72_torch_up.npz"))
+    shapes = collections.OrderedDict((k, v) for k, v in load_keys("drn_d_22").items() if k != "up.weight")
+    sd = recipe.make_state_dict(shapes, seed=int(fx["seed"]))
+    x = recipe.make_frames(1, int(fx["hw"][0]), int(fx["hw"][1]), seed=1234 + int(fx["seed"]))
+    lp, seg = drn_oracle.drnseg_forward(sd, x, use_torch_up=True)
+    assert np.abs(seg.numpy() - fx["seg"]).max() <= 1e-4 * np.abs(fx["seg"]).max()
+    assert np.abs(lp.numpy() - fx["logprob"]).max() <= 1e-4 * np.abs(fx["seg"]).max()
+    assert (lp.argmax(1).numpy() == fx["labels"]).mean() >= 0.9999

@@ -28,6 +28,7 @@ struct drnb200_head_plan {
   float* d_shift;    // [32] bias, zero padded
   float* d_logits;   // [N,h,w,32] fp32 scratch
   int fused_ok;      // labels-only calls run head_fused_kernel
+  int up_mode;       // 0 = fixed-bilinear ConvTranspose2d (default), 1 = UpsamplingBilinear2d (align_corners=True)
   const void* fmap_ptr;
   CUtensorMap fmap;  // [N,h,w,C] activations, box {64, 16, 8, 1}
 };
@@ -405,6 +406,52 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
   }
 }
 
+// use_torch_up=True (semantic_seg.py:144-145): nn.UpsamplingBilinear2d(scale_factor=8) == bilinear interpolation with
+// align_corners=True.  src = y * (h-1)/(H-1); the four neighbours are blended as torch's CPU kernel does it
+// (rows first: w0*(a0*v00 + a1*v01) + w1*(a0*v10 + a1*v11), all fp32).  Thread = one output pixel; the low-res logits
+// [N,h,w,32] are L2-resident.  Parity path only (labels, log-probs); the fused kernel serves the default `up`.
+template <int CLS_MAX>
+__global__ void __launch_bounds__(256)
+up_aligned_kernel(const float* __restrict__ L, int N, int h, int w, int classes, uint8_t* __restrict__ labels,
+                  float* __restrict__ logprob) {
+  const int H = 8 * h, W = 8 * w;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  if (x >= W) return;
+  const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const float fy = sy * (float)y, fx = sx * (float)x;
+  const int i0 = (int)fy, j0 = (int)fx;
+  const int i1 = min(i0 + 1, h - 1), j1 = min(j0 + 1, w - 1);
+  const float w1 = fy - (float)i0, w0 = 1.f - w1, a1 = fx - (float)j0, a0 = 1.f - a1;
+  const float* r00 = L + (((size_t)n * h + i0) * w + j0) * HEAD_CP;
+  const float* r01 = L + (((size_t)n * h + i0) * w + j1) * HEAD_CP;
+  const float* r10 = L + (((size_t)n * h + i1) * w + j0) * HEAD_CP;
+  const float* r11 = L + (((size_t)n * h + i1) * w + j1) * HEAD_CP;
+  float v[CLS_MAX];
+  float best = -INFINITY;
+  int arg = 0;
+#pragma unroll
+  for (int c = 0; c < CLS_MAX; ++c) {
+    if (c < classes) {
+      const float top = __fmaf_rn(a1, __ldg(r01 + c), __fmul_rn(a0, __ldg(r00 + c)));
+      const float bot = __fmaf_rn(a1, __ldg(r11 + c), __fmul_rn(a0, __ldg(r10 + c)));
+      v[c] = __fmaf_rn(w1, bot, __fmul_rn(w0, top));
+      if (v[c] > best) { best = v[c]; arg = c; }
+    }
+  }
+  const size_t pix = ((size_t)n * H + y) * W + x;
+  if (labels != nullptr) labels[pix] = (uint8_t)arg;
+  if (logprob != nullptr) {
+    float ssum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CLS_MAX; ++c)
+      if (c < classes) ssum += expf(v[c] - best);
+    const float lse = best + logf(ssum);
+#pragma unroll
+    for (int c = 0; c < CLS_MAX; ++c)
+      if (c < classes) logprob[(((size_t)n * classes + c) * H + y) * W + x] = v[c] - lse;
+  }
+}
+
 // [N,h,w,32] float32 -> [N,classes,h,w] float32  (DRNSeg.forward()[1])
 __global__ void logits_to_nchw_kernel(const float* __restrict__ L, int N, int h, int w, int classes,
                                       float* __restrict__ out) {
@@ -531,17 +578,33 @@ static int head_fused_launch(drnb200_head_plan* plan, const void* x, uint8_t* la
   return DRNB200_OK;
 }
 
-extern "C" int drnb200_head_plan_fused(const drnb200_head_plan* plan) { return (plan && plan->fused_ok) ? 1 : 0; }
+extern "C" int drnb200_head_plan_fused(const drnb200_head_plan* plan) {
+  return (plan && plan->fused_ok && plan->up_mode == 0) ? 1 : 0;
+}
+
+extern "C" int drnb200_head_plan_set_upsample(drnb200_head_plan* plan, int mode) {
+  DRN_REQUIRE(plan, "head_plan_set_upsample: null plan");
+  DRN_REQUIRE(mode == DRNB200_UP_TRANSPOSED || mode == DRNB200_UP_ALIGNED, "head_plan_set_upsample: unknown mode %d", mode);
+  plan->up_mode = mode;
+  return DRNB200_OK;
+}
 
 extern "C" int drnb200_head_forward(drnb200_head_plan* plan, const void* x_nhwc, uint8_t* labels,
                                     float* seg_logits, float* logprob, void* stream) {
   DRN_REQUIRE(plan && x_nhwc, "head_forward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (labels && !seg_logits && !logprob && plan->fused_ok)      // the fast path: one kernel, labels only
+  if (labels && !seg_logits && !logprob && plan->fused_ok && plan->up_mode == 0)   // the fast path: one kernel, labels only
     return head_fused_launch(plan, x_nhwc, labels, st);
   int rc = drnb200_conv_forward(plan->conv, x_nhwc, nullptr, plan->d_logits, stream);
   if (rc) return rc;
-  if (labels || logprob) {
+  if ((labels || logprob) && plan->up_mode == DRNB200_UP_ALIGNED) {
+    const dim3 blocks((8 * plan->w + 255) / 256, 8 * plan->h, plan->N);
+    if (plan->classes <= 19)
+      up_aligned_kernel<19><<<blocks, 256, 0, st>>>(plan->d_logits, plan->N, plan->h, plan->w, plan->classes, labels, logprob);
+    else
+      up_aligned_kernel<32><<<blocks, 256, 0, st>>>(plan->d_logits, plan->N, plan->h, plan->w, plan->classes, labels, logprob);
+    DRN_CUDA(cudaGetLastError());
+  } else if (labels || logprob) {
     const dim3 blocks((8 * plan->w + UP_BW - 1) / UP_BW, (8 * plan->h + UP_BH - 1) / UP_BH, plan->N);
     if (plan->classes <= 19)
       up_argmax_kernel<19><<<blocks, 256, 0, st>>>(plan->d_logits, plan->N, plan->h, plan->w,

@@ -652,6 +652,8 @@ class Engine:
             ffi.check(ffi.lib().drnb200_head_plan_create(
                 C.byref(hdl), N, h, w, seg.in_channels, seg.out_channels, self.act_dtype,
                 ffi.ptr(self.seg_w), ffi.ptr(self.seg_b), ffi.stream_ptr()), "head_plan_create")
+            if getattr(self.m, "use_torch_up", False):      # nn.UpsamplingBilinear2d(scale_factor=8), semantic_seg.py:144-145
+                ffi.check(ffi.lib().drnb200_head_plan_set_upsample(hdl, 1), "head_plan_set_upsample")
             p = self.head_plans[k] = hdl
         return p
 

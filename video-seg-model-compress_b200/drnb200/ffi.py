@@ -56,6 +56,7 @@ SIGNATURES = {
     "drnb200_head_forward": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "drnb200_head_plan_destroy": (None, [_P]),
     "drnb200_head_plan_fused": (C.c_int, [_P]),
+    "drnb200_head_plan_set_upsample": (C.c_int, [_P, C.c_int]),
     "drnb200_confusion": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "drnb200_colorize": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, C.c_float, _P, _P]),
     "drnb200_labels_to_i64": (C.c_int, [_P, C.c_int64, _P, _P]),

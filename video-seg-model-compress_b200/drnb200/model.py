@@ -168,13 +168,10 @@ class DRNSeg(nn.Module):
 
     def _eng(self, where=None):
         """engine of the CUDA device `where` (a tensor, a device, or None = the parameters' device)"""
-        if self.use_torch_up:
-            raise ffi.Drnb200Error("use_torch_up=True (UpsamplingBilinear2d, align_corners) is not part "
-                                   "of the accelerated path; the reference's default is the fixed "
-                                   "ConvTranspose2d (semantic_seg.py:147-152)")
-        up = self.up.weight
-        if tuple(up.shape[2:]) != (16, 16) or self.up.stride != (8, 8) or self.up.padding != (4, 4):
-            raise ffi.Drnb200Error("`up` must be ConvTranspose2d(k=16, s=8, p=4)")
+        if not self.use_torch_up:
+            up = self.up.weight
+            if tuple(up.shape[2:]) != (16, 16) or self.up.stride != (8, 8) or self.up.padding != (4, 4):
+                raise ffi.Drnb200Error("`up` must be ConvTranspose2d(k=16, s=8, p=4)")
         if isinstance(where, torch.Tensor):
             where = where.device
         dev = torch.device(where) if where is not None else next(self.parameters()).device
@@ -186,7 +183,8 @@ class DRNSeg(nn.Module):
                 eng = self._engines.get(key)
                 if eng is None:
                     ffi.lib()                      # fail loudly if the CUDA library is missing
-                    if not torch.equal(up.detach()[:, 0].cpu().double(), _bilinear_kernel(up.shape[0], 16)):
+                    if not self.use_torch_up and not torch.equal(self.up.weight.detach()[:, 0].cpu().double(),
+                                                                 _bilinear_kernel(self.up.weight.shape[0], 16)):
                         raise ffi.Drnb200Error(
                             "`up.weight` differs from fill_up_weights (semantic_seg.py:115-124): the fused head "
                             "hard-codes the analytic bilinear kernel and would ignore this checkpoint's values")
