@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <atomic>
 #include "../../include/drnb200.h"
 
 namespace drnb200 {
@@ -25,6 +26,15 @@ int  cuda_fail(cudaError_t e, const char* what);
   do {                                                                   \
     if (!(cond)) { drnb200::set_error(__VA_ARGS__); return DRNB200_E_ARG; } \
   } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is PER DEVICE: a once-per-process flag would leave every other GPU of
+// the process at the 48 KB default (launches there fail with "invalid argument").  One atomic bit mask per call site.
+inline bool attr_needed_on_this_device(std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (done.fetch_or(bit) & bit) == 0;
+}
 
 // Diagnostic knobs that make results INVALID (DRNB200_DBG timing probes, DRNB200_HALO=1) exist only in a
 // `make EXTRA=-DDRNB200_DIAG` build: the shipping library never reads them, so a stray variable in a job's
@@ -272,6 +282,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+// 16 lanes x 32 consecutive fp32 columns in the mma C-fragment layout (measured, tools/probe_tmem_ld.cu): for every
+// block k of 8 columns, thread t holds v[4k+0..1] = (lane t/4, columns 8k + 2(t%4), +1) and v[4k+2..3] = (lane t/4 + 8,
+// same columns).  After packing each pair to 16 bits the registers ARE stmatrix/ldmatrix fragments.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// four 8x8 b16 matrices, transposed on the way: shared-memory row i of matrix m (address from lane 8m+i, 16 bytes)
+// receives COLUMN i of the fragment matrix whose element (r, 2c..2c+1) thread 4r+c holds
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t saddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(r0),
+               "r"(r1), "r"(r2), "r"(r3)
+               : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(saddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");

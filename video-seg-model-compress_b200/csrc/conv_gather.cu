@@ -378,15 +378,14 @@ static int gather_launch(GatherParams& p, int act_dtype, GMapCache& cache, cudaS
   p.ring = (int)std::min<size_t>(G_HRING, (kMaxSmem - fixed - (size_t)p.n_abuf * p.abuf_bytes) / p.halo_stride);
   if (p.ring < 2) { set_error("conv_gather: buffers do not fit shared memory"); return DRNB200_E_ARG; }
   const size_t smem = fixed + (size_t)p.n_abuf * p.abuf_bytes + (size_t)p.ring * p.halo_stride;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[act_dtype]) {
+  static std::atomic<unsigned long long> attr_done[2];
+  if (attr_needed_on_this_device(attr_done[act_dtype])) {
     if (act_dtype == DRNB200_BF16)
       DRN_CUDA(cudaFuncSetAttribute(conv_gather_kernel<DRNB200_BF16>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     else
       DRN_CUDA(cudaFuncSetAttribute(conv_gather_kernel<DRNB200_F16>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    attr_done[act_dtype] = true;
   }
   int dev = 0, sms = 148;
   DRN_CUDA(cudaGetDevice(&dev));

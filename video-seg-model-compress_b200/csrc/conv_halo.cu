@@ -407,12 +407,10 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   const int ks = (int)(p.pitch / 32u);
 #define DRN_HALO_LAUNCH1(DT, KS, RES)                                                                          \
   do {                                                                                                         \
-    static bool attr = false;                                                                                  \
-    if (!attr) {                                                                                               \
+    static std::atomic<unsigned long long> attr;                                                               \
+    if (attr_needed_on_this_device(attr))                                                                      \
       DRN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<DT, KS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)kMaxSmem));                                                           \
-      attr = true;                                                                                             \
-    }                                                                                                          \
     conv_halo_kernel<DT, KS, RES><<<grid, H_THREADS, kMaxSmem, st>>>(cache->map, p);                           \
   } while (0)
 #define DRN_HALO_LAUNCH(DT, KS)                        \

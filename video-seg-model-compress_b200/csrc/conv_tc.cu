@@ -443,9 +443,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             // <= k - D - 1, D - 1 of them newer than that one, so it has drained once at most D - 1 are still reading
             if (elect_one()) {
               bulk_wait_group_read<D - 1>();
-              if (p.has_res) {                      // residual chunk [32 px][128 couts] straight into the slot
-                mbar_arrive_expect_tx(&sync->rfull[b], kEpBufBytes);
+              if (p.has_res) {                      // residual chunk [32 px][128 couts] straight into the slot: two
+                mbar_arrive_expect_tx(&sync->rfull[b], kEpBufBytes);        // SWIZZLE_128B boxes of 64 couts
                 tma_load_4d(&tmap_r, &sync->rfull[b], stg + b * kEpBufBytes, p.res_coff + c.ot * 128, cx, cy, c.n);
+                tma_load_4d(&tmap_r, &sync->rfull[b], stg + b * kEpBufBytes + kEpBufBytes / 2,
+                            p.res_coff + c.ot * 128 + 64, cx, cy, c.n);
               } else {
                 mbar_arrive(&sync->sfree[b]);
               }
@@ -456,9 +458,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               const uint32_t kb = k - D, bb = kb & (kEpRing - 1);
               mbar_wait(&sync->sdone[bb], (kb / kEpRing) & 1u);
               if (elect_one()) {
-                if (!(p.dbg & 8))
+                if (!(p.dbg & 8)) {
                   tma_store_4d(&tmap_y, stg + bb * kEpBufBytes, hist_ot[kb % D] * 128, hist_cx[kb % D],
                                hist_cy[kb % D], hist_n[kb % D]);
+                  tma_store_4d(&tmap_y, stg + bb * kEpBufBytes + kEpBufBytes / 2, hist_ot[kb % D] * 128 + 64,
+                               hist_cx[kb % D], hist_cy[kb % D], hist_n[kb % D]);
+                }
                 bulk_commit_group();
               }
               __syncwarp();
@@ -473,6 +478,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           if (elect_one()) {
             tma_store_4d(&tmap_y, stg + bb * kEpBufBytes, hist_ot[kb % D] * 128, hist_cx[kb % D], hist_cy[kb % D],
                          hist_n[kb % D]);
+            tma_store_4d(&tmap_y, stg + bb * kEpBufBytes + kEpBufBytes / 2, hist_ot[kb % D] * 128 + 64, hist_cx[kb % D],
+                         hist_cy[kb % D], hist_n[kb % D]);
             bulk_commit_group();
           }
           __syncwarp();
@@ -480,26 +487,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         if (elect_one()) bulk_wait_group<0>();     // all stores complete before the CTA retires
         __syncwarp();
       } else {
-        // ---- epilogue groups
+        // ---- epilogue groups.  The accumulator is read with tcgen05.ld.16x256b (mma C-fragment layout: thread t holds
+        // couts t/4 + {0, 8} (+16 with the second load) x pixel pairs), so after BN / residual / ReLU and packing to 16
+        // bits the registers ARE stmatrix fragments: stmatrix.trans writes 16-byte rows of 8 couts per pixel, the
+        // residual arrives the same way through ldmatrix.trans.  One chunk costs a warp 4 + 4 shared-memory
+        // instructions of 512 bytes each instead of 32 + 32 two-byte accesses (which occupied the 128 B/clk pipe for 64
+        // bytes each: the shared-memory pipe is what bounds this kernel, profiles/r02_conv_row_accumulator_layouts.txt).
+        // Slot layout: two SWIZZLE_128B boxes [32 px][64 couts]; a pixel's 16-byte chunk c sits at c ^ (pixel & 7).
         const int grp = (warp - 2) >> 2;
-        const int cl = q * 32 + lane;              // cout inside the 128-cout tile
+        const int g = lane >> 2;                   // cout row of this thread inside an 8-cout group
         const int nch = p.ep_nch;
+        const uint32_t half_off = (uint32_t)(q >> 1) * (kEpBufBytes / 2);       // couts 0-63 | 64-127 of the tile
+        const uint32_t cbase = (uint32_t)(q & 1) * 4u;                         // first 16-byte chunk of this warp's 32 couts
+        const uint32_t row_off = (uint32_t)(8 * (lane >> 3) + (lane & 7)) * 128u;   // matrix m = lane/8 -> pixels 8m..8m+7
         uint32_t k0 = 0;                           // flat chunk index of the tile's first chunk
         // the tile's decode and BN affine are fetched one tile ahead: on tiles with few live K-blocks this global
         // round trip (plus the integer divisions of the decode) would otherwise sit on every warp's critical path
         TileCoord c_next = decode_tile(p, blockIdx.x < p.total_tiles ? blockIdx.x : 0);
-        float sc_next = __ldg(p.scale + c_next.ot * 128 + cl), sh_next = __ldg(p.shift + c_next.ot * 128 + cl);
+        float sc_next[4], sh_next[4];
+#pragma unroll
+        for (int cg = 0; cg < 4; ++cg) {
+          sc_next[cg] = __ldg(p.scale + c_next.ot * 128 + q * 32 + 8 * cg + g);
+          sh_next[cg] = __ldg(p.shift + c_next.ot * 128 + q * 32 + 8 * cg + g);
+        }
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
           const TileCoord c = c_next;
-          const float sc = sc_next, sh = sh_next;
+          float sc[4], sh[4];
+          int relu[4];
+#pragma unroll
+          for (int cg = 0; cg < 4; ++cg) {
+            sc[cg] = sc_next[cg]; sh[cg] = sh_next[cg];
+            relu[cg] = (c.ot * 128 + q * 32 + 8 * cg + g) < p.relu_n;
+          }
           if (t + (int)gridDim.x < p.total_tiles) {
             c_next = decode_tile(p, t + gridDim.x);
-            sc_next = __ldg(p.scale + c_next.ot * 128 + cl);
-            sh_next = __ldg(p.shift + c_next.ot * 128 + cl);
+#pragma unroll
+            for (int cg = 0; cg < 4; ++cg) {
+              sc_next[cg] = __ldg(p.scale + c_next.ot * 128 + q * 32 + 8 * cg + g);
+              sh_next[cg] = __ldg(p.shift + c_next.ot * 128 + q * 32 + 8 * cg + g);
+            }
           }
           const bool live = c.je > c.jb;
-          const int co = c.ot * 128 + cl;
-          const int relu = co < p.relu_n;
           int qq = (int)(((uint32_t)grp - k0) & (uint32_t)(NG - 1));   // first chunk of this tile owned by this group
           if (live) {
             mbar_wait(&sync->tfull[acc], acc_phase);
@@ -509,25 +537,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           for (; qq < nch; qq += NG) {
             const uint32_t k = k0 + (uint32_t)qq;
             const uint32_t b = k & (kEpRing - 1);
-            uint8_t* buf = stg + b * kEpBufBytes;
+            const uint32_t slot = smem_u32(stg + b * kEpBufBytes) + half_off + row_off;
+            uint32_t va[16], vb[16];               // couts g, g+8 | g+16, g+24  x  4 blocks of 8 pixels
+            if (live) {
+              tmem_ld_16x256b_x4(t_addr + (uint32_t)(qq * kEpChunkPx), va);
+              tmem_ld_16x256b_x4(t_addr + (16u << 16) + (uint32_t)(qq * kEpChunkPx), vb);
+            }
             // the slot's previous store has drained; with a residual, its chunk [32 px][128 couts] has landed (TMA)
             if (p.has_res) mbar_wait(&sync->rfull[b], (k / kEpRing) & 1u);
             else mbar_wait(&sync->sfree[b], (k / kEpRing) & 1u);
-            uint32_t v[32];
             if (live) {
-              tmem_ld32(t_addr + (uint32_t)(qq * kEpChunkPx), v);
               tmem_ld_wait();
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = 0u;
+              for (int i = 0; i < 16; ++i) { va[i] = 0u; vb[i] = 0u; }
             }
-            uint16_t* col = reinterpret_cast<uint16_t*>(buf) + cl;   // [pixel][128 couts]
-            if (!(p.dbg & 16)) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float r = p.has_res ? Act<DT>::to_f32(col[i * 128]) : 0.f;
-                col[i * 128] = Act<DT>::from_f32(finish<DT>(__uint_as_float(v[i]), sc, sh, r, relu));
+            for (int cg = 0; cg < 4; ++cg) {
+              const uint32_t addr = slot + (((cbase + (uint32_t)cg) ^ (uint32_t)(lane & 7)) << 4);
+              uint32_t r[4] = {0u, 0u, 0u, 0u}, o[4];
+              if (p.has_res) ldmatrix_x4_trans(addr, r[0], r[1], r[2], r[3]);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {     // pixel block kk: pixels 8kk + 2(lane%4), +1
+                const uint32_t* src = cg < 2 ? va : vb;
+                const int idx = 4 * kk + 2 * (cg & 1);
+                const float r_lo = p.has_res ? Act<DT>::to_f32((uint16_t)(r[kk] & 0xFFFFu)) : 0.f;
+                const float r_hi = p.has_res ? Act<DT>::to_f32((uint16_t)(r[kk] >> 16)) : 0.f;
+                o[kk] = pack2<DT>(finish<DT>(__uint_as_float(src[idx]), sc[cg], sh[cg], r_lo, relu[cg]),
+                                  finish<DT>(__uint_as_float(src[idx + 1]), sc[cg], sh[cg], r_hi, relu[cg]));
               }
+              stmatrix_x4_trans(addr, o[0], o[1], o[2], o[3]);
             }
             fence_proxy_async_smem();              // st.shared -> visible to the TMA store
             __syncwarp();
@@ -817,7 +856,7 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   return DRNB200_OK;
 }
 
-// output-shaped NHWC tensor, box = one staged chunk (128 couts x ep_cw x ep_ch pixels), no swizzle;
+// output-shaped NHWC tensor, box = HALF a staged chunk (64 couts x ep_cw x ep_ch pixels), SWIZZLE_128B (two per chunk);
 // `cpitch` = channels per pixel of the tensor the pointer lives in (the residual may be a channel sub-range)
 static int encode_out_tmap(drnb200_conv_plan* plan, CUtensorMap* map, const void* ptr, int cpitch) {
   const ConvParams& p = plan->p;
@@ -829,12 +868,12 @@ static int encode_out_tmap(drnb200_conv_plan* plan, CUtensorMap* map, const void
   cuuint64_t gdim[4] = {(cuuint64_t)cpitch, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.N};
   cuuint64_t gstr[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)p.OW * cpitch * 2,
                         (cuuint64_t)p.OH * p.OW * cpitch * 2};
-  cuuint32_t box[4] = {128, (cuuint32_t)p.ep_cw, (cuuint32_t)p.ep_ch, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)p.ep_cw, (cuuint32_t)p.ep_ch, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMapDataType dt = plan->d.act_dtype == DRNB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                              : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = fn(map, dt, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(out) failed with CUresult %d (Cout=%d OW=%d OH=%d N=%d box=%u,%u,%u)",

@@ -566,12 +566,12 @@ static int head_fused_launch(drnb200_head_plan* plan, const void* x, uint8_t* la
   DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = std::min(p.total_tiles, sms);
   if (grid == 0) return DRNB200_OK;
-  static bool attr[2] = {false, false};
+  static std::atomic<unsigned long long> attr[2];
   if (plan->act_dtype == DRNB200_BF16) {
-    if (!attr[0]) { DRN_CUDA(cudaFuncSetAttribute(head_fused_kernel<DRNB200_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHfMaxSmem)); attr[0] = true; }
+    if (attr_needed_on_this_device(attr[0])) DRN_CUDA(cudaFuncSetAttribute(head_fused_kernel<DRNB200_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHfMaxSmem));
     head_fused_kernel<DRNB200_BF16><<<grid, HF_THREADS, smem, st>>>(plan->fmap, p);
   } else {
-    if (!attr[1]) { DRN_CUDA(cudaFuncSetAttribute(head_fused_kernel<DRNB200_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHfMaxSmem)); attr[1] = true; }
+    if (attr_needed_on_this_device(attr[1])) DRN_CUDA(cudaFuncSetAttribute(head_fused_kernel<DRNB200_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHfMaxSmem));
     head_fused_kernel<DRNB200_F16><<<grid, HF_THREADS, smem, st>>>(plan->fmap, p);
   }
   DRN_CUDA(cudaGetLastError());

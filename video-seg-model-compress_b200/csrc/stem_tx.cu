@@ -474,11 +474,9 @@ int stem_tx_forward(StemTxState* s, const void* x, int src_kind, const uint16_t*
       act_dtype == DRNB200_BF16
           ? (src_kind == SRC_U8 ? stem_tx_kernel<DRNB200_BF16, SRC_U8> : stem_tx_kernel<DRNB200_BF16, SRC_F32>)
           : (src_kind == SRC_U8 ? stem_tx_kernel<DRNB200_F16, SRC_U8> : stem_tx_kernel<DRNB200_F16, SRC_F32>);
-  static bool attr[2][2] = {{false, false}, {false, false}};
-  if (!attr[act_dtype][src_kind]) {
+  static std::atomic<unsigned long long> attr[2][2];
+  if (attr_needed_on_this_device(attr[act_dtype][src_kind]))
     DRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr[act_dtype][src_kind] = true;
-  }
   int dev = 0, sms = 148;
   DRN_CUDA(cudaGetDevice(&dev));
   DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
