@@ -731,6 +731,31 @@ def test_frames_on_another_device_and_data_parallel():
     assert set(model._engines) == {0, 1}                           # replicas reused the original's engines
 
 
+@pytest.mark.parametrize("mode", ["pinned", "wc", "huge"])
+def test_host_staging_buffers(mode):
+    """drnb200_host_alloc / HostBuffer: pinned, write-combined and huge-page-registered frame buffers are valid sources
+    of asynchronous H2D copies (and, for the cacheable modes, targets of D2H copies); foreign pointers are refused"""
+    from drnb200.frameio import HostBuffer
+    hb = HostBuffer((3, 64, 128, 3), torch.uint8, mode)
+    ref = recipe.make_u8_frames(3, 64, 128, seed=4)
+    hb.tensor.copy_(ref)
+    d = torch.empty_like(ref, device=dev())
+    d.copy_(hb.tensor, non_blocking=True)
+    torch.cuda.synchronize()
+    assert torch.equal(d.cpu(), ref)
+    if mode != "wc":                                       # write-combined memory is for H2D sources only
+        hb.tensor.zero_()
+        hb.tensor.copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
+        assert torch.equal(hb.tensor, ref)
+    hb.close()
+    hb.close()                                             # idempotent
+    assert ffi.lib().drnb200_host_free(C.c_void_p(0x1000)) != 0      # not ours
+    assert ffi.lib().drnb200_host_free(None) == 0
+    with pytest.raises(ffi.Drnb200Error):
+        HostBuffer((4,), torch.uint8, "mapped")
+
+
 def test_input_validation():
     model, sd, x = _gate_case("drn_d_22", 64, 128, 1, False, "fp16", seed=11)
     with pytest.raises(ffi.Drnb200Error):
