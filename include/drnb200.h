@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRNB200_VERSION 108
+#define DRNB200_VERSION 109
 
 /* error codes */
 #define DRNB200_OK          0
@@ -229,6 +229,17 @@ int drnb200_confusion(const uint8_t* pred, const void* label, int label_is_i64, 
 int drnb200_colorize(const uint8_t* labels, int64_t n_px, const uint8_t* palette, int n_colors,
                      const uint8_t* frames_or_null, float alpha, uint8_t* out_rgb, void* stream);
 int drnb200_labels_to_i64(const uint8_t* labels, int64_t n, int64_t* out, void* stream);
+
+/* Frame resize, the step before the ingest in the video caller (seg_video_old.py:125-128: torchvision T.Resize on the PIL
+ * frame = Pillow's 8-bit BILINEAR resampler, src/libImaging/Resample.c).  src uint8 [N,Hs,Ws,3] -> dst uint8 [N,H,W,3],
+ * bit-identical to PIL: horizontal pass into the uint8 scratch `tmp` [N,Hs,W,3], then the vertical pass; per pass
+ * ss = 2^21 + sum_t pixel * k[t], out = clip8(ss >> 22).  The caller passes Pillow's coefficient tables per axis as
+ * int32 (normalize_coeffs_8bpc: (int)(k * 2^22 +- 0.5)): xmin[W], xcnt[W], xk[W*kx]; kx == 0 means "no horizontal pass"
+ * (Ws == W), ky == 0 likewise; `tmp` may be NULL unless both passes run.  All pointers are device pointers. */
+int drnb200_resize_u8(const uint8_t* src, int N, int Hs, int Ws, uint8_t* dst, int H, int W,
+                      const int32_t* xmin, const int32_t* xcnt, const int32_t* xk, int kx,
+                      const int32_t* ymin, const int32_t* ycnt, const int32_t* yk, int ky,
+                      uint8_t* tmp, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pinned HOST staging buffers for frames (H2D) and label maps (D2H) — the two PCIe ends of the path.  Replaces the

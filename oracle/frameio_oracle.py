@@ -49,3 +49,43 @@ def overlay(pred, frames_u8_nhwc, alpha=0.6, palette=CITYSCAPE_PALETTE):
     col = colorize(pred, palette).astype(np.float32)
     f = np.asarray(frames_u8_nhwc).astype(np.float32)
     return np.rint(a * col + b * f).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------ frame resize
+# seg_video_old.py:125-128 resizes every decoded frame with torchvision `T.Resize((h, w))` on a PIL image, i.e.
+# `Image.resize((w, h), BILINEAR)` — Pillow's 8-bit resampler (third-party, not in /root/reference; Pillow 12.2.0 here,
+# src/libImaging/Resample.c, unchanged since 3.4): precompute_coeffs() in double (oracle/ms_oracle.bilinear_coeffs),
+# then normalize_coeffs_8bpc(): k_int = (int)(k * 2^22 +- 0.5), horizontal pass over the source rows the vertical pass
+# needs (ss = 2^21; ss += pixel * k_int; out = clip8(ss >> 22)) into a uint8 temporary, then the vertical pass likewise.
+PRECISION_BITS = 32 - 8 - 2
+
+
+def coeffs_8bpc(in_size, out_size):
+    """-> (xmin int32 [out], count int32 [out], k int32 [out, ksize])"""
+    from oracle import ms_oracle
+    xmin, cnt, kk = ms_oracle.bilinear_coeffs(in_size, out_size)
+    scaled = kk * float(1 << PRECISION_BITS)
+    ki = np.where(kk < 0, np.trunc(-0.5 + scaled), np.trunc(0.5 + scaled)).astype(np.int64).astype(np.int32)
+    return xmin, cnt, ki
+
+
+def _pass_8bpc(a, out_size):
+    """one 8-bit Pillow pass along axis -2 of a uint8 [..., L, C] array"""
+    in_size = a.shape[-2]
+    xmin, cnt, ki = coeffs_8bpc(in_size, out_size)
+    ss = np.full(a.shape[:-2] + (out_size, a.shape[-1]), 1 << (PRECISION_BITS - 1), np.int64)
+    for t in range(ki.shape[1]):
+        live = (t < cnt)[:, None]
+        idx = np.minimum(xmin + t, in_size - 1)
+        ss = np.where(live, ss + a[..., idx, :].astype(np.int64) * ki[:, t][:, None], ss)
+    return np.clip(ss >> PRECISION_BITS, 0, 255).astype(np.uint8)
+
+
+def resize_u8(frames, height, width):
+    """uint8 [N,H,W,3] -> uint8 [N,height,width,3], = T.Resize((height, width)) on each PIL frame"""
+    a = np.asarray(frames, np.uint8)
+    if a.shape[2] != width:
+        a = _pass_8bpc(a, width)                                   # horizontal first (axis -2 is W)
+    if a.shape[1] != height:
+        a = np.swapaxes(_pass_8bpc(np.swapaxes(a, 1, 2), height), 1, 2)
+    return np.ascontiguousarray(a)

@@ -969,6 +969,34 @@ def test_colorize_and_overlay_bit_exact():
     assert drnb200.colorize(torch.zeros(0, 4, dtype=torch.uint8, device=dev())).shape == (0, 4, 3)
 
 
+def test_frame_resize_bit_exact_against_pil():
+    """drnb200.resize_frames == T.Resize on the PIL frame (seg_video_old.py:125-128), bit for bit: files produced by
+    real torchvision / PIL for down-, up- and single-axis scaling of a real video frame, plus the oracle on a batch
+    of random frames at the caller's own size (640x1138 -> 300x300), plus guard bands around the output"""
+    from oracle import frameio_oracle
+    fx = np.load(golden("frame_resize.npz"))
+    src = torch.from_numpy(fx["src"]).to(dev())[None]
+    for i, (h, w) in enumerate(fx["sizes"]):
+        got = drnb200.resize_frames(src, (int(h), int(w)))
+        assert np.array_equal(got[0].cpu().numpy(), fx["dst%d" % i]), (h, w)
+    assert torch.equal(drnb200.resize_frames(src, (160, 284)), src)                  # same size: a copy
+    rng = np.random.RandomState(9)
+    frames = rng.randint(0, 256, size=(2, 640, 1138, 3), dtype=np.uint8)
+    ref = frameio_oracle.resize_u8(frames, 300, 300)
+    got = drnb200.resize_frames(torch.from_numpy(frames).to(dev()), (300, 300))
+    assert np.array_equal(got.cpu().numpy(), ref)
+    # straight into the fused ingest: resized uint8 frames -> labels (304x304 like the reference, seg_video_old.py:127)
+    model, sd, _ = _gate_case("drn_d_22", 64, 128, 1, True, "fp16", seed=24)
+    fio = np.load(golden("frameio.npz"))
+    model.set_ingest(fio["mean"], fio["std"])
+    small = drnb200.resize_frames(torch.from_numpy(frames).to(dev()), (300, 304))     # W % 16 == 0 for the uint8 ingest
+    lab = model.predict(small)
+    assert lab.shape == (2, 304, 304)
+    assert torch.equal(lab, model.predict(frameio_oracle.ingest(small.cpu().numpy(), fio["mean"], fio["std"]).to(dev())))
+    with pytest.raises(ffi.Drnb200Error):
+        drnb200.resize_frames(torch.from_numpy(frames), (300, 300))                  # CPU tensor: no fallback
+
+
 def test_full_size_uint8_ingest():
     """1024x2048: the fused uint8 ingest equals the float path fed with the reference's transform of the same frames"""
     from oracle import frameio_oracle

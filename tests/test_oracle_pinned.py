@@ -158,3 +158,20 @@ def test_oracle_use_torch_up_matches_the_real_reference():
     assert np.abs(seg.numpy() - fx["seg"]).max() <= 1e-4 * np.abs(fx["seg"]).max()
     assert np.abs(lp.numpy() - fx["logprob"]).max() <= 1e-4 * np.abs(fx["seg"]).max()
     assert (lp.argmax(1).numpy() == fx["labels"]).mean() >= 0.9999
+
+
+def test_oracle_frame_resize_matches_pil():
+    """T.Resize on a PIL frame (seg_video_old.py:125-128) = Pillow's 8-bit BILINEAR resampler: the restatement in
+    oracle/frameio_oracle.py against files produced by real torchvision / PIL (tests/golden/gen_golden_resize.py)"""
+    from oracle import frameio_oracle
+    fx = np.load(golden("frame_resize.npz"))
+    for i, (h, w) in enumerate(fx["sizes"]):
+        got = frameio_oracle.resize_u8(fx["src"][None], int(h), int(w))[0]
+        assert np.array_equal(got, fx["dst%d" % i]), (h, w)
+    # the int32 tables the device path uploads are the oracle's
+    from drnb200 import frameio as product
+    import torch
+    lo, cnt, ki, ksize = product._resize_axis_tables(284, 100, torch.device("cpu"))
+    olo, ocnt, oki = frameio_oracle.coeffs_8bpc(284, 100)
+    assert np.array_equal(lo.numpy(), olo) and np.array_equal(cnt.numpy(), ocnt) and np.array_equal(ki.numpy(), oki)
+    assert ksize == oki.shape[1]

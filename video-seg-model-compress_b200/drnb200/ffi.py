@@ -63,6 +63,8 @@ SIGNATURES = {
     "drnb200_ms_accumulate": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
                                         _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]),
     "drnb200_ms_argmax": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "drnb200_resize_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int,
+                                    _P, _P, _P, C.c_int, _P, _P]),
     "drnb200_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64, C.c_int]),
     "drnb200_host_free": (C.c_int, [_P]),
 }

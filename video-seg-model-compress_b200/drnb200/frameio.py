@@ -70,6 +70,48 @@ def overlay(labels, frames, alpha=0.6, palette=CITYSCAPE_PALETTE):
     return _colorize(labels, frames, alpha, palette)
 
 
+_resize_tables = {}
+
+
+def _resize_axis_tables(in_size, out_size, device):
+    """Pillow's 8-bit coefficient tables of one axis on the device (normalize_coeffs_8bpc), or None if the size is kept"""
+    if in_size == out_size:
+        return None
+    key = (in_size, out_size, str(device))
+    t = _resize_tables.get(key)
+    if t is None:
+        from .multiscale import bilinear_coeffs
+        lo, cnt, kk = bilinear_coeffs(in_size, out_size)
+        scaled = kk * float(1 << 22)
+        ki = np.where(kk < 0, np.trunc(-0.5 + scaled), np.trunc(0.5 + scaled)).astype(np.int64).astype(np.int32)
+        t = _resize_tables[key] = (torch.from_numpy(lo).to(device), torch.from_numpy(cnt).to(device),
+                                   torch.from_numpy(np.ascontiguousarray(ki)).to(device), ki.shape[1])
+    return t
+
+
+def resize_frames(frames, size):
+    """uint8 CUDA frames [N,Hs,Ws,3] -> uint8 [N,h,w,3], bit-identical to `T.Resize((h, w))` on every PIL frame
+    (seg_video_old.py:125-128: Pillow's 8-bit BILINEAR resampler with its widened support when downscaling)."""
+    if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4
+            and frames.shape[3] == 3):
+        raise ffi.Drnb200Error("resize_frames needs a uint8 CUDA tensor [N,H,W,3]; there is no CPU path")
+    h, w = int(size[0]), int(size[1])
+    frames = frames.contiguous()
+    N, Hs, Ws, _ = frames.shape
+    dev = frames.device
+    with torch.cuda.device(dev):
+        out = torch.empty((N, h, w, 3), dtype=torch.uint8, device=dev)
+        tx, ty = _resize_axis_tables(Ws, w, dev), _resize_axis_tables(Hs, h, dev)
+        tmp = torch.empty((N, Hs, w, 3), dtype=torch.uint8, device=dev) if tx is not None and ty is not None else None
+        nul = (None, None, None, 0)
+        xlo, xcnt, xk, kx = tx if tx is not None else nul
+        ylo, ycnt, yk, ky = ty if ty is not None else nul
+        ffi.check(ffi.lib().drnb200_resize_u8(ffi.ptr(frames), N, Hs, Ws, ffi.ptr(out), h, w, ffi.ptr(xlo), ffi.ptr(xcnt),
+                                              ffi.ptr(xk), kx, ffi.ptr(ylo), ffi.ptr(ycnt), ffi.ptr(yk), ky, ffi.ptr(tmp),
+                                              ffi.stream_ptr()), "resize_u8")
+    return out
+
+
 class HostBuffer:
     """Pinned host staging buffer for frames (H2D) or label maps (D2H), allocated by the library
     (`drnb200_host_alloc`): ``mode`` = "pinned" (cudaHostAlloc, what ``Tensor.pin_memory()`` gives), "wc"
