@@ -778,6 +778,12 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   //      single live K-block stay at ~4700 cycles with no math and no stores at all (pipeline skeleton).
   p.ep_groups = 2;
   if (mode == MODE_T) {
+    // 1x1 convs with a residual and very few live K-blocks per tile (the 512 -> 2048 expand convs of the Bottleneck
+    // networks at 75 % sparsity: 2 of 8) are pure streaming work: four groups = eight staging slots keep twice as many
+    // residual loads / output stores in flight (DRN-D-54 conv3 launches: 2.675 -> 2.578 ms per step, measured); every
+    // other layer loses main-ring stages to the extra staging and is slower with four
+    const double avg_live = (double)plan->h_row_ptr[p.n_ot] / std::max(1, p.n_ot);
+    if (p.taps == 1 && p.has_res && avg_live <= 4.0) p.ep_groups = 4;
     static const char* env_ng = getenv("DRNB200_NG");        // A/B knob: force 2 or 4 epilogue groups
     if (env_ng && (env_ng[0] == '2' || env_ng[0] == '4')) p.ep_groups = env_ng[0] - '0';
   }
