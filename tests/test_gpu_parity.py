@@ -338,13 +338,6 @@ def _build(arch, sd, masks, act):
     return m
 
 
-def _per_layer_report(model, sd, x):
-    """max error of every layer output against the oracle taps, relative to that layer's range"""
-    taps = {}
-    drn_oracle.drnseg_forward(sd, x, taps=taps)
-    return taps
-
-
 E2E = [("fwd_drn_d_22_64x128_dense.npz", "drn_d_22"), ("fwd_drn_d_22_64x128_block75.npz", "drn_d_22"),
        ("fwd_drn_d_38_32x64_block75.npz", "drn_d_38"), ("fwd_drn_d_54_32x64_dense.npz", "drn_d_54"),
        ("fwd_drn_c_26_32x64_dense.npz", "drn_c_26")]
