@@ -575,6 +575,48 @@ def test_frame_sizes_that_are_not_multiples_of_8(hw):
     assert tuple(lab.shape) == (1, 8 * h8, 8 * w8) == tuple(ref_lab.shape)
 
 
+def test_random_frame_shapes_sweep():
+    """seeded sweep over frame shapes and batch sizes (any H >= 8, W % 4 == 0): output shapes follow the reference's
+    rounding (8*ceil(H/8) x 8*ceil(W/8)), logits within tolerance, predict() == argmax(forward()[0]) bit for bit, and
+    labels equal to the oracle's except for near-tie pixels.  This is a SHAPE-robustness test (ragged tiles of every
+    kernel: halo / gather / row-halo / per-tap convs, the head's 15x7-cell tiles with half cells at all four borders),
+    so the label bound is what 16-bit storage rounding alone explains: at most max(3 pixels, 1.5 x the count the CPU
+    emulation of fp16 storage gives on the same frame) — e.g. 121x1028: 135 pixels on the GPU, 127 emulated (99.898 %
+    vs 99.904 %); pixels whose fp32 margin exceeds the logit tolerance must agree exactly."""
+    rng = np.random.RandomState(2026)
+    model, sd, _ = _gate_case("drn_d_22", 64, 128, 1, True, "fp16", seed=33)
+    worst = 1.0
+    for case in range(10):
+        n = int(rng.randint(1, 4))
+        h = int(rng.randint(8, 200))
+        w = 4 * int(rng.randint(2, 100))
+        if case == 0:
+            h, w = 8, 8                                       # the smallest accepted frame
+        if case == 1:
+            h, w = 121, 1028                                  # one row-halo tile plus 1 pixel at 1/8 resolution
+        x = recipe.make_frames(n, h, w, seed=500 + case)
+        ref_lp, ref_seg = drn_oracle.drnseg_forward(sd, x)
+        with torch.no_grad():
+            lp, seg = model(x.to(dev()))
+            lab = model.predict(x.to(dev()))
+        h8, w8 = -(-h // 8), -(-w // 8)
+        assert tuple(lab.shape) == (n, 8 * h8, 8 * w8) == tuple(ref_lp.shape[0:1] + ref_lp.shape[2:]), (n, h, w)
+        assert torch.equal(torch.max(lp, 1)[1].to(torch.uint8), lab), (n, h, w)
+        assert rel_err(seg.cpu(), ref_seg) <= LOGIT_RTOL and rel_err(lp.cpu(), ref_lp) <= LOGIT_RTOL, (n, h, w)
+        ref_lab = torch.max(ref_lp, 1)[1]
+        differ = int((lab.cpu().long() != ref_lab).sum())
+        npx = lab.numel()
+        worst = min(worst, 1.0 - differ / npx)
+        emu_lp, _ = drn_oracle.drnseg_forward(sd, x, quant=lambda role, key, t: t.half().float())
+        emu = int((emu_lp.argmax(1) != ref_lab).sum())
+        assert differ <= max(3, int(1.5 * emu) + 3), (n, h, w, differ, emu, npx)
+        top2 = ref_lp.topk(2, dim=1)[0]
+        confident = (top2[:, 0] - top2[:, 1]) > LOGIT_RTOL * ref_seg.abs().max()
+        assert torch.equal(lab.cpu().long()[confident], ref_lab[confident]), (n, h, w)
+    record("random frame shapes sweep (10 shapes, D-22 BlockPruner 75%): worst case", act="fp16", frames="8x8 .. 200x400",
+           label_agreement=worst)
+
+
 def test_bf16_storage_is_the_measured_exception():
     """bf16 activation storage (north_star's nominal layout).  Logits, log-probs and mIoU gates hold; the 99.9 % label
     gate does NOT on random-init networks and cannot with bf16 conv operands: replaying the engine's roundings inside
