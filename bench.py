@@ -10,7 +10,8 @@ data-path collective (weights/tile lists replicated, "weak" scaling); the only N
 the 19x19 int64 confusion matrix at the end of the evaluation, inside the timed region.
 One JSON line is printed by rank 0.  Beside the contract keys it carries
   roofline / roofline_all_convs / roofline_head   fractions of the BURST peaks for event-timed kernels (+ of sustained)
-  e2e / e2e_uint8_frames     pinned host frames -> H2D -> predict -> labels D2H every step, with the per-rank copy rates
+  e2e / e2e_uint8_frames     drnb200.FramePipeline: pinned host frames -> H2D -> predict -> labels D2H every step, with
+                             the per-rank copy rates
   host_ceiling               H2D GB/s with ALL ranks copying and no kernels: the bound of e2e scaling on this host
   bf16                       the same workload with bf16 activation storage (frames/s + label agreement)
   sustained                  >= 3 s of back-to-back steps: frames/s, SM clock, power, throttle reasons
@@ -344,83 +345,40 @@ def timed_steps(ctx, model, meter, x, gt, steps, warmup):
     return ctx.max_over_ranks([ms])[0]
 
 
-def e2e_measure(ctx, model, hx, B, H, W, steps, eval_mode=None):
-    """hx: pinned host batch (float32 NCHW, or uint8 NHWC with set_ingest).  Every step copies ITS input from pinned
-    host memory (copy stream), runs predict (main stream) and copies the result back to pinned host memory (D2H
-    stream); three input buffers so the copies of the next steps overlap the kernels of this one.
-    The result is the uint8 label map (video mode, seg_video.py), or — `eval_mode` = (meter, gt) — the 19x19 confusion
-    matrix accumulated on the device (evaluation mode, semantic_seg.py test(): 2.9 kB per step).
+def e2e_measure(ctx, model, frames, steps, eval_mode=None, host_mode="pinned"):
+    """End to end through the repo's public API, `drnb200.FramePipeline` (the data flow of the reference's video caller):
+    every step copies ITS input batch from pinned host memory, runs `DRNSeg.predict` and copies the result back to
+    pinned host memory; three batches in flight, copies on their own streams.  `frames`: one host batch (float32 NCHW,
+    or uint8 NHWC with set_ingest) that stands for the decoded frames.  The result is the uint8 label map (video mode,
+    seg_video.py) or — `eval_mode` = (meter, gt) — the 19x19 confusion matrix accumulated on the device (evaluation
+    mode, semantic_seg.py test(): 2.9 kB per step).
     -> (ms for `steps` steps, mean H2D GB/s of this rank's copies, mean D2H GB/s)"""
-    dev = ctx.dev
-    NB = 3
-    copy_stream = torch.cuda.Stream(device=dev)
-    d2h_stream = torch.cuda.Stream(device=dev)
-    main_stream = torch.cuda.current_stream()
-    hl = [torch.empty((B, H, W), dtype=torch.uint8).pin_memory() for _ in range(NB)]
-    hh = [torch.empty((19, 19), dtype=torch.int64).pin_memory() for _ in range(NB)]
-    xd = [torch.empty(hx.shape, dtype=hx.dtype, device=dev) for _ in range(NB)]
-    ready = [torch.cuda.Event() for _ in range(NB)]
-    consumed = [torch.cuda.Event() for _ in range(NB)]
-    d2h_done = [torch.cuda.Event() for _ in range(NB)]
-    keep = [None] * NB
-    copy_ev = []
+    import drnb200
+    pipe = drnb200.FramePipeline(model, tuple(frames.shape), frames.dtype, output="hist" if eval_mode else "labels",
+                                 meter=eval_mode, depth=3, host_mode=host_mode, device=ctx.dev)
+    for b in range(pipe.depth):
+        pipe.staging(b).copy_(frames)              # "decoded" frames sit in the pinned staging buffers
 
-    def e2e_run(n_steps, record):
-        for s_ in range(n_steps + 1):
-            if s_ < n_steps:                      # stage batch s_ on the copy stream
-                b = s_ % NB
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(consumed[b])
-                    if record:
-                        a0 = torch.cuda.Event(enable_timing=True)
-                        a0.record(copy_stream)
-                    xd[b].copy_(hx, non_blocking=True)
-                    if record:
-                        a1 = torch.cuda.Event(enable_timing=True)
-                        a1.record(copy_stream)
-                        copy_ev.append(("h2d", a0, a1))
-                    ready[b].record(copy_stream)
-            if s_ >= 1:                           # segment batch s_-1 on the main stream
-                b = (s_ - 1) % NB
-                main_stream.wait_event(ready[b])
-                main_stream.wait_event(d2h_done[b])      # labels of batch s_-1-NB are on the host:
-                keep[b] = labels = model.predict(xd[b])  # their device buffer may be recycled
-                if eval_mode is not None:
-                    eval_mode[0].update(labels, eval_mode[1])
-                consumed[b].record(main_stream)
-                with torch.cuda.stream(d2h_stream):      # labels go back on their own stream so the
-                    d2h_stream.wait_event(consumed[b])   # next batch's kernels are not queued behind PCIe
-                    if record:
-                        a0 = torch.cuda.Event(enable_timing=True)
-                        a0.record(d2h_stream)
-                    if eval_mode is not None:
-                        hh[b].copy_(eval_mode[0].hist, non_blocking=True)
-                    else:
-                        hl[b].copy_(labels, non_blocking=True)
-                    if record:
-                        a1 = torch.cuda.Event(enable_timing=True)
-                        a1.record(d2h_stream)
-                        copy_ev.append(("d2h", a0, a1))
-                    d2h_done[b].record(d2h_stream)
+    def feed(n):
+        return (pipe.staging(k) for k in range(n))
 
-    for b in range(NB):
-        consumed[b].record(main_stream)
-        d2h_done[b].record(main_stream)
-    e2e_run(NB, False)
+    for _ in pipe.run(feed(pipe.depth)):
+        pass
     ctx.barrier()
+    pipe.record_copies = True
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     f0.record()
-    e2e_run(steps, True)
-    main_stream.wait_stream(d2h_stream)               # the last labels have reached the host
+    got = 0
+    for res in pipe.run(feed(steps)):              # every result has reached pinned host memory when it is yielded
+        got += 1
     f1.record()
     ctx.barrier()
     wall = time.perf_counter() - t0
+    assert got == steps
     ms = max(f0.elapsed_time(f1), 1e3 * wall)
-    h2d = [a.elapsed_time(b) for k, a, b in copy_ev if k == "h2d"]
-    d2h = [a.elapsed_time(b) for k, a, b in copy_ev if k == "d2h"]
-    h2d_gbs = hx.numel() * hx.element_size() / (sum(h2d) / len(h2d) * 1e-3) / 1e9
-    d2h_gbs = (19 * 19 * 8 if eval_mode is not None else B * H * W) / (sum(d2h) / len(d2h) * 1e-3) / 1e9
+    h2d_gbs, d2h_gbs = pipe.copy_rates()
+    pipe.close()
     return ms, h2d_gbs, d2h_gbs
 
 
@@ -577,7 +535,7 @@ def main():
         # ---- e2e: host frames -> H2D -> predict -> D2H labels, through the public API (DRNSeg.predict)
         hbuf = HostBuffer((B, 3, H, W), torch.float32, args.host_mode)
         hbuf.tensor.copy_(x.cpu())
-        e2e_ms, h2d_gbs, d2h_gbs = e2e_measure(ctx, model, hbuf.tensor, B, H, W, args.steps)
+        e2e_ms, h2d_gbs, d2h_gbs = e2e_measure(ctx, model, hbuf.tensor, args.steps, host_mode=args.host_mode)
         ceiling, ceiling_d2h = host_ceiling(ctx, hbuf.tensor, B * H * W) if extras else (None, None)
         # the same through the fused frame ingest: uint8 HWC frames as cv2 delivers them, the
         # reference's ToTensor + Normalize (info.json statistics) applied inside the stem kernel
@@ -586,9 +544,10 @@ def main():
             model.set_ingest(INFO_MEAN, INFO_STD)
             hu8 = HostBuffer((B, H, W, 3), torch.uint8, args.host_mode)
             hu8.tensor.copy_(synthetic.make_u8_frames(B, H, W, seed=1234 + rank))
-            e2e_u8_ms, u8_h2d, u8_d2h = e2e_measure(ctx, model, hu8.tensor, B, H, W, args.steps)
+            e2e_u8_ms, u8_h2d, u8_d2h = e2e_measure(ctx, model, hu8.tensor, args.steps, host_mode=args.host_mode)
             if extras:
-                e2e_ev_ms, ev_h2d, _ = e2e_measure(ctx, model, hu8.tensor, B, H, W, args.steps, eval_mode=(meter, gt))
+                e2e_ev_ms, ev_h2d, _ = e2e_measure(ctx, model, hu8.tensor, args.steps, eval_mode=(meter, gt),
+                                                   host_mode=args.host_mode)
             hu8.close()
         clocks = sampler.finish()
         e2e_ms, e2e_u8_ms, e2e_ev_ms = ctx.max_over_ranks([e2e_ms, e2e_u8_ms or 0.0, e2e_ev_ms or 0.0])

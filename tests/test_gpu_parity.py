@@ -1032,6 +1032,56 @@ def test_frame_resize_bit_exact_against_pil():
         drnb200.resize_frames(torch.from_numpy(frames), (300, 300))                  # CPU tensor: no fallback
 
 
+def test_frame_pipeline_matches_direct_calls():
+    """drnb200.FramePipeline (the reference's FrameCapture data flow, seg_video_old.py:110-203, as a three-stage
+    streaming object): per-batch results arrive in order and equal resize_frames -> predict -> overlay called directly;
+    more batches than buffers; float32 frames; evaluation mode returns the running confusion matrix"""
+    from oracle import frameio_oracle
+    model, sd, _ = _gate_case("drn_d_22", 64, 128, 1, True, "fp16", seed=25)
+    fio = np.load(golden("frameio.npz"))
+    model.set_ingest(fio["mean"], fio["std"])
+    rng = np.random.RandomState(11)
+    batches = [rng.randint(0, 256, size=(2, 90, 150, 3), dtype=np.uint8) for _ in range(7)]
+    direct_lab, direct_ov = [], []
+    for b in batches:
+        small = drnb200.resize_frames(torch.from_numpy(b).to(dev()), (64, 96))
+        lab = model.predict(small)
+        direct_lab.append(lab.cpu().clone())
+        direct_ov.append(drnb200.overlay(lab, small, 0.6).cpu().clone())
+    pipe = drnb200.FramePipeline(model, (2, 90, 150, 3), torch.uint8, resize_to=(64, 96), output="labels", depth=3)
+    got = [r.clone() for r in pipe.run(iter(batches))]
+    assert len(got) == 7 and all(torch.equal(a, b) for a, b in zip(got, direct_lab))
+    # frames decoded straight into the staging buffers, fewer batches than buffers, then reuse of the same object
+    def feed():
+        for k in range(2):
+            pipe.staging(k).copy_(torch.from_numpy(batches[k]))
+            yield pipe.staging(k)
+    got = [r.clone() for r in pipe.run(feed())]
+    assert len(got) == 2 and torch.equal(got[0], direct_lab[0]) and torch.equal(got[1], direct_lab[1])
+    assert list(pipe.run(iter([]))) == []
+    pipe.close()
+    ov = drnb200.FramePipeline(model, (2, 90, 150, 3), torch.uint8, resize_to=(64, 96), output="overlay", depth=2,
+                               host_mode="wc")
+    got = [r.clone() for r in ov.run(iter(batches[:5]))]
+    assert all(torch.equal(a, b) for a, b in zip(got, direct_ov[:5]))
+    ov.close()
+    # float32 NCHW frames (the reference's tensor) and the evaluation flow
+    x = recipe.make_frames(2, 64, 128, seed=77)
+    gt = torch.randint(0, 19, (2, 64, 128), generator=torch.Generator().manual_seed(5)).to(torch.uint8).to(dev())
+    meter = drnb200.ConfusionMeter(19, dev())
+    ev = drnb200.FramePipeline(model, (2, 3, 64, 128), torch.float32, output="hist", meter=(meter, gt))
+    hists = [r.clone() for r in ev.run(iter([x, x, x]))]
+    want = drnb200.ConfusionMeter(19, dev())
+    want.update(model.predict(x.to(dev())), gt)
+    assert torch.equal(hists[0], want.hist.cpu()) and torch.equal(hists[2], 3 * want.hist.cpu())
+    ev.close()
+    with pytest.raises(ffi.Drnb200Error):
+        list(drnb200.FramePipeline(model, (2, 3, 64, 128), torch.float32).run(iter([x[:1]])))     # wrong batch shape
+    with pytest.raises(ffi.Drnb200Error):
+        drnb200.FramePipeline(model, (2, 3, 64, 128), torch.float32, resize_to=(32, 32))          # resize needs uint8
+    del frameio_oracle
+
+
 def test_full_size_uint8_ingest():
     """1024x2048: the fused uint8 ingest equals the float path fed with the reference's transform of the same frames"""
     from oracle import frameio_oracle

@@ -14,8 +14,9 @@ from . import checkpoint
 from .checkpoint import load_checkpoint, normalize_state_dict, masks_from_zeros
 from .frameio import CITYSCAPE_PALETTE, colorize, overlay, load_info, resize_frames, HostBuffer
 from . import multiscale
+from .pipeline import FramePipeline
 from .multiscale import predict_ms, test_ms
 
 __all__ = ["DRNSeg", "fill_up_weights", "drn", "pruners", "ffi", "ConfusionMeter", "fast_hist",
-           "per_class_iu", "shard_frames", "frameio", "CITYSCAPE_PALETTE", "colorize", "overlay", "load_info", "resize_frames", "HostBuffer",
+           "per_class_iu", "shard_frames", "frameio", "CITYSCAPE_PALETTE", "colorize", "overlay", "load_info", "resize_frames", "HostBuffer", "FramePipeline",
            "ingest_lut", "multiscale", "predict_ms", "test_ms", "checkpoint", "load_checkpoint", "normalize_state_dict", "masks_from_zeros"]
