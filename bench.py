@@ -532,7 +532,7 @@ def main():
         launches = (eng.launches_per_forward + 1) * args.steps
         miou = meter.miou()
 
-        # ---- e2e: host frames -> H2D -> predict -> D2H labels, through the public API (DRNSeg.predict)
+        # ---- e2e: host frames -> H2D -> predict -> D2H labels, through the public API (drnb200.FramePipeline)
         hbuf = HostBuffer((B, 3, H, W), torch.float32, args.host_mode)
         hbuf.tensor.copy_(x.cpu())
         e2e_ms, h2d_gbs, d2h_gbs = e2e_measure(ctx, model, hbuf.tensor, args.steps, host_mode=args.host_mode)
