@@ -282,7 +282,7 @@ struct __align__(16) HFSync {
   uint32_t cand[HF_LBUF][HF_CX * HF_CY];   // per cell: classes that can win somewhere in the cell (cell_candidates)
 };
 
-template <int DT>
+template <int DT, bool PRUNE>
 __global__ void __launch_bounds__(HF_THREADS, 1)
 head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -393,7 +393,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
         o.w = inside ? __fadd_rn(__uint_as_float(v[4 * c4 + 3]), sync->bias[4 * c4 + 3]) : 0.f;
         *reinterpret_cast<float4*>(dst + 4 * c4) = o;
       }
-      if (p.prune) {
+      if (PRUNE) {
         named_bar_sync(2, 128);                             // all 128 low-res pixels of the tile are staged
         if (m < HF_CX * HF_CY) {                            // one cell per thread
           const int cy = m / HF_CX, cx = m - cy * HF_CX;
@@ -401,8 +401,6 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
           sync->cand[lb][m] = cell_candidates<19>(p00, p00 + HF_CP, p00 + HF_LW * HF_CP, p00 + (HF_LW + 1) * HF_CP,
                                                   p.classes);
         }
-      } else if (m < HF_CX * HF_CY) {
-        sync->cand[lb][m] = 0xFFFFFFFFu;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sync->lfull[lb]);
@@ -435,7 +433,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
             float V0[19], V1[19];
             up_vertical<19>(tile + (((yy >> 3) + 1) * HF_LW + cx + 1) * HF_CP, HF_LW * HF_CP, yy & 7, V0, V1);
             uint32_t lo, hi;
-            up_argmax8<19>(V0, V1, p.classes, sync->cand[lb][(yy >> 3) * HF_CX + cx], lo, hi);
+            up_argmax8<19>(V0, V1, p.classes, PRUNE ? sync->cand[lb][(yy >> 3) * HF_CX + cx] : 0xFFFFFFFFu, lo, hi);
             uint8_t* row = p.labels + ((size_t)n * H + y) * W;
             if (x0 >= 0) *reinterpret_cast<uint32_t*>(row + x0) = lo;
             if (x0 + 4 < W) *reinterpret_cast<uint32_t*>(row + x0 + 4) = hi;
@@ -619,14 +617,13 @@ static int head_fused_launch(drnb200_head_plan* plan, const void* x, uint8_t* la
   DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = std::min(p.total_tiles, sms);
   if (grid == 0) return DRNB200_OK;
-  static std::atomic<unsigned long long> attr[2];
-  if (plan->act_dtype == DRNB200_BF16) {
-    if (attr_needed_on_this_device(attr[0])) DRN_CUDA(cudaFuncSetAttribute(head_fused_kernel<DRNB200_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHfMaxSmem));
-    head_fused_kernel<DRNB200_BF16><<<grid, HF_THREADS, smem, st>>>(plan->fmap, p);
-  } else {
-    if (attr_needed_on_this_device(attr[1])) DRN_CUDA(cudaFuncSetAttribute(head_fused_kernel<DRNB200_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHfMaxSmem));
-    head_fused_kernel<DRNB200_F16><<<grid, HF_THREADS, smem, st>>>(plan->fmap, p);
-  }
+  static std::atomic<unsigned long long> attr[4];
+  void (*kern)(const CUtensorMap, const HeadFusedParams) =
+      plan->act_dtype == DRNB200_BF16 ? (p.prune ? head_fused_kernel<DRNB200_BF16, true> : head_fused_kernel<DRNB200_BF16, false>)
+                                      : (p.prune ? head_fused_kernel<DRNB200_F16, true> : head_fused_kernel<DRNB200_F16, false>);
+  if (attr_needed_on_this_device(attr[(plan->act_dtype == DRNB200_BF16 ? 0 : 2) + (p.prune ? 1 : 0)]))
+    DRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHfMaxSmem));
+  kern<<<grid, HF_THREADS, smem, st>>>(plan->fmap, p);
   DRN_CUDA(cudaGetLastError());
   return DRNB200_OK;
 }
