@@ -50,6 +50,37 @@ inline int diag_env(const char* name) {
 #endif
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// The persistent kernels of one forward run back to back on one stream, each reading what the previous one wrote.
+// launch_chained() lets the NEXT kernel's CTAs start on an SM as soon as the previous kernel's CTA there has exited:
+// barrier init, TMEM allocation, descriptor prefetch and the kernel's own launch latency then overlap the previous
+// kernel's tail.  Every such kernel executes griddep_launch() first and griddep_wait() before its first access to
+// global memory that another kernel writes (both are no-ops when the launch carries no attribute).
+// DRNB200_PDL=0 launches with plain stream order (A/B switch; results are identical either way).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const int on = [] { const char* v = getenv("DRNB200_PDL"); return v ? atoi(v) : 1; }();
+  return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------ 16-bit storage helpers
 template <int DT> struct Act;  // DT = DRNB200_BF16 / DRNB200_F16
 template <> struct Act<DRNB200_BF16> {

@@ -110,6 +110,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
   GSync* sync = reinterpret_cast<GSync*>(wsm + G_MAX_KB * 32 * 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  griddep_launch();
   if (tid == 0) {
     tma_prefetch_desc(&tmap_x);
     for (int b = 0; b < G_HRING; ++b) {
@@ -130,6 +131,7 @@ conv_gather_kernel(const __grid_constant__ CUtensorMap tmap_x, const GatherParam
     tmem_alloc(&sync->tmem_base, G_TMEM_COLS);
     tmem_relinquish();
   }
+  griddep_wait();       // up to here the CTA overlapped the previous kernel's tail; no global memory was read yet
   if (tid < 32) {   // BN affine -> shared memory: with ~all of the SM's storage carved out as shared memory
                     // there is no L1 left, and 32 global loads per pixel thread per tile would go to L2
     sync->scale[tid] = tid < p.Cout ? __ldg(p.scale + tid) : 0.f;
@@ -392,8 +394,8 @@ static int gather_launch(GatherParams& p, int act_dtype, GMapCache& cache, cudaS
   DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = std::min(p.total_tiles, sms);
   if (grid == 0) return DRNB200_OK;
-  if (act_dtype == DRNB200_BF16) conv_gather_kernel<DRNB200_BF16><<<grid, G_THREADS, smem, st>>>(cache.map, p);
-  else conv_gather_kernel<DRNB200_F16><<<grid, G_THREADS, smem, st>>>(cache.map, p);
+  if (act_dtype == DRNB200_BF16) launch_chained(conv_gather_kernel<DRNB200_BF16>, grid, G_THREADS, smem, st, cache.map, p);
+  else launch_chained(conv_gather_kernel<DRNB200_F16>, grid, G_THREADS, smem, st, cache.map, p);
   DRN_CUDA(cudaGetLastError());
   return DRNB200_OK;
 }

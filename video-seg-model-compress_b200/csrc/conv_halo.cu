@@ -108,22 +108,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p)
   HSync* sync = reinterpret_cast<HSync*>(wsm + ((9u * p.w_tile_bytes + 1023u) & ~1023u));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     for (int b = 0; b < p.ring; ++b) { mbar_init(&sync->h_full[b], 1); mbar_init(&sync->h_empty[b], 1); }
     for (int a = 0; a < H_ACC; ++a) { mbar_init(&sync->t_full[a], 1); mbar_init(&sync->t_empty[a], 4); }
     mbar_init(&sync->w_full, 1);
-    for (int k = 0; k < 9; ++k) sync->taps[k] = k < p.n_kb ? __ldg(p.kblk + k) : 0;
     mbar_fence_init();
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 64) {     // BN affine -> shared memory (read by every pixel thread)
-    const int ch = threadIdx.x - 64;
-    sync->scale[ch] = ch < p.Cout ? __ldg(p.scale + ch) : 0.f;
-    sync->shift[ch] = ch < p.Cout ? __ldg(p.shift + ch) : 0.f;
   }
   if (warp == 1) {
     tmem_alloc(&sync->tmem_base, H_TMEM_COLS);
     tmem_relinquish();
+  }
+  griddep_wait();       // up to here the CTA overlapped the previous kernel's tail; no global memory was read yet
+  if (threadIdx.x < 9) sync->taps[threadIdx.x] = (int)threadIdx.x < p.n_kb ? __ldg(p.kblk + threadIdx.x) : 0;
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 64) {     // BN affine -> shared memory (read by every pixel thread)
+    const int ch = threadIdx.x - 64;
+    sync->scale[ch] = ch < p.Cout ? __ldg(p.scale + ch) : 0.f;
+    sync->shift[ch] = ch < p.Cout ? __ldg(p.shift + ch) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -411,7 +413,7 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
     if (attr_needed_on_this_device(attr))                                                                      \
       DRN_CUDA(cudaFuncSetAttribute(conv_halo_kernel<DT, KS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     (int)kMaxSmem));                                                           \
-    conv_halo_kernel<DT, KS, RES><<<grid, H_THREADS, kMaxSmem, st>>>(cache->map, p);                           \
+    launch_chained(conv_halo_kernel<DT, KS, RES>, grid, H_THREADS, kMaxSmem, st, cache->map, p);                     \
   } while (0)
 #define DRN_HALO_LAUNCH(DT, KS)                        \
   do {                                                 \

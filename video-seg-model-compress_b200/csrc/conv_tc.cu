@@ -127,6 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  griddep_launch();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap);
@@ -160,6 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     tmem_alloc(&sync->tmem_base, kTmemCols);
     tmem_relinquish();
   }
+  griddep_wait();       // up to here the CTA overlapped the previous kernel's tail; no global memory was read yet
   if (MODE == MODE_P || PIX) {
     for (int ch = threadIdx.x; ch < 512; ch += tc_threads(NG)) {
       sync->scale[ch] = ch < p.Cout ? __ldg(p.scale + ch) : 0.f;
@@ -777,6 +779,10 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   //      tiles as fast as four (layer-5/6 residual convs 0.129/0.249 -> 0.115/0.228 ms with either), and tiles with a
   //      single live K-block stay at ~4700 cycles with no math and no stores at all (pipeline skeleton).
   p.ep_groups = 2;
+  static const char* env_row = getenv("DRNB200_ROW");       // A/B knob: "0" keeps the per-tap pipeline
+  // ROW variant: 3x3 stride-1 convs over 64-channel K-blocks whose tile is one 256-pixel row segment
+  const bool row_ok = mode == MODE_T && p.taps == 9 && d.stride == 1 && p.tile_ci == 64 && d.dilation <= 4 &&
+                      TW == kRowPx && TH == 1 && !(env_row && env_row[0] == '0');
   if (mode == MODE_T) {
     // 1x1 convs with a residual and very few live K-blocks per tile (the 512 -> 2048 expand convs of the Bottleneck
     // networks at 75 % sparsity: 2 of 8) are pure streaming work: four groups = eight staging slots keep twice as many
@@ -784,6 +790,11 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
     // other layer loses main-ring stages to the extra staging and is slower with four
     const double avg_live = (double)plan->h_row_ptr[p.n_ot] / std::max(1, p.n_ot);
     if (p.taps == 1 && p.has_res && avg_live <= 4.0) p.ep_groups = 4;
+    // row-halo 3x3 convs that read a residual and keep <= 12 K-blocks per tile (layers 4 and 5 at 75 %) wait for their
+    // residual chunks, not for MMAs: eight slots in flight win 4-6 % there (4.0.conv2 0.0505 -> 0.0476 ms, 5.1.conv2
+    // 0.0878 -> 0.0831, same-box A/B); with 18 live K-blocks (6.1.conv2) or a projection instead of a residual the
+    // shallower row ring costs 4-14 %
+    if (row_ok && p.has_res && !p.proj && avg_live <= 12.0 && d.acc_layout != 2) p.ep_groups = 4;
     static const char* env_ng = getenv("DRNB200_NG");        // A/B knob: force 2 or 4 epilogue groups
     if (env_ng && (env_ng[0] == '2' || env_ng[0] == '4')) p.ep_groups = env_ng[0] - '0';
   }
@@ -792,14 +803,11 @@ int conv_tc_setup(drnb200_conv_plan* plan) {
   stages = std::max(2, std::min(stages, kMaxStages));
   p.stages = stages;
   plan->smem_bytes = kMaxSmem;
-  // ---- ROW variant: 3x3 stride-1 convs over 64-channel K-blocks whose tile is one 256-pixel row segment
-  static const char* env_row = getenv("DRNB200_ROW");       // A/B knob: "0" keeps the per-tap pipeline
   p.row_mode = 0;
   static const int env_dbg = diag_env("DRNB200_DBG");        // -DDRNB200_DIAG builds only: timing diagnostics of the ROW
   p.dbg = env_dbg;                                           // mainloop (results invalid): 1 no weight loads, 2 no row loads,
                                                              // 4 no residual loads, 8 no output stores, 16 no epilogue math
-  if (mode == MODE_T && p.taps == 9 && d.stride == 1 && p.tile_ci == 64 && d.dilation <= 4 && TW == kRowPx &&
-      TH == 1 && !(env_row && env_row[0] == '0')) {
+  if (row_ok) {
     static const char* env_ring = getenv("DRNB200_ROW_RING");   // "x,w" ring sizes for tuning
     int xr = p.ep_groups == 4 ? 2 : 3, wr = 5;            // four groups: 64 KB of staging, shallower row ring
     if (env_ring && sscanf(env_ring, "%d,%d", &xr, &wr) != 2) { xr = 3; wr = 5; }
@@ -990,19 +998,19 @@ int conv_tc_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   const bool bf = plan->d.act_dtype == DRNB200_BF16;
 #define DRN_LAUNCH(M)                                                                                   \
   do {                                                                                                  \
-    if (bf) conv_tc_kernel<M, DRNB200_BF16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p); \
-    else    conv_tc_kernel<M, DRNB200_F16><<<grid, block, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);  \
+    if (bf) launch_chained(conv_tc_kernel<M, DRNB200_BF16>, grid, block, plan->smem_bytes, st, plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p); \
+    else    launch_chained(conv_tc_kernel<M, DRNB200_F16>, grid, block, plan->smem_bytes, st, plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);  \
   } while (0)
 #define DRN_LAUNCH_T(ROWV, NGV)                                                                                       \
   do {                                                                                                                \
     const dim3 blk(tc_threads(NGV));                                                                                  \
-    if (bf) conv_tc_kernel<MODE_T, DRNB200_BF16, ROWV, NGV><<<grid, blk, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p); \
-    else    conv_tc_kernel<MODE_T, DRNB200_F16, ROWV, NGV><<<grid, blk, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);  \
+    if (bf) launch_chained(conv_tc_kernel<MODE_T, DRNB200_BF16, ROWV, NGV>, grid, blk, plan->smem_bytes, st, plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p); \
+    else    launch_chained(conv_tc_kernel<MODE_T, DRNB200_F16, ROWV, NGV>, grid, blk, plan->smem_bytes, st, plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);  \
   } while (0)
   if (plan->tc_mode == MODE_T && p.row_mode && p.pix_mode) {
     const dim3 blk(tc_threads(2));
-    if (bf) conv_tc_kernel<MODE_T, DRNB200_BF16, true, 2, true><<<grid, blk, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);
-    else    conv_tc_kernel<MODE_T, DRNB200_F16, true, 2, true><<<grid, blk, plan->smem_bytes, st>>>(plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);
+    if (bf) launch_chained(conv_tc_kernel<MODE_T, DRNB200_BF16, true, 2, true>, grid, blk, plan->smem_bytes, st, plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);
+    else    launch_chained(conv_tc_kernel<MODE_T, DRNB200_F16, true, 2, true>, grid, blk, plan->smem_bytes, st, plan->tmap, plan->tmap_y, plan->tmap_r, plan->tmap_x2, p);
   } else if (plan->tc_mode == MODE_T && (p.row_mode || p.ep_groups == 4)) {
     if (p.row_mode && p.ep_groups == 4) DRN_LAUNCH_T(true, 4);
     else if (p.row_mode) DRN_LAUNCH_T(true, 2);

@@ -293,6 +293,7 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
   __shared__ HFSync sync_s;
   HFSync* sync = &sync_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_x);
     for (int i = 0; i < HF_STAGES; ++i) { mbar_init(&sync->full[i], 1); mbar_init(&sync->empty[i], 1); }
@@ -301,12 +302,13 @@ head_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const HeadFusedPar
     mbar_init(&sync->wfull, 1);
     mbar_fence_init();
   }
-  if (threadIdx.x < 32) sync->bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
   if (threadIdx.x < HF_LBUF) sync->chunk[threadIdx.x] = 0;
   if (warp == 1) {
     tmem_alloc(&sync->tmem_base, HF_ACC * 32);
     tmem_relinquish();
   }
+  griddep_wait();       // up to here the CTA overlapped the previous kernel's tail; no global memory was read yet
+  if (threadIdx.x < 32) sync->bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -623,7 +625,7 @@ static int head_fused_launch(drnb200_head_plan* plan, const void* x, uint8_t* la
                                       : (p.prune ? head_fused_kernel<DRNB200_F16, true> : head_fused_kernel<DRNB200_F16, false>);
   if (attr_needed_on_this_device(attr[(plan->act_dtype == DRNB200_BF16 ? 0 : 2) + (p.prune ? 1 : 0)]))
     DRN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHfMaxSmem));
-  kern<<<grid, HF_THREADS, smem, st>>>(plan->fmap, p);
+  launch_chained(kern, grid, HF_THREADS, smem, st, plan->fmap, p);
   DRN_CUDA(cudaGetLastError());
   return DRNB200_OK;
 }

@@ -149,6 +149,7 @@ stem_tx_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   TxSync* sync = &sync_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  griddep_launch();
   if (tid == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_y);
@@ -158,9 +159,6 @@ stem_tx_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     mbar_init(&sync->w_full, 1);
     mbar_fence_init();
   }
-  if (tid < 16) { sync->scale[tid] = __ldg(p.scale + tid); sync->shift[tid] = __ldg(p.shift + tid); }
-  if (SRC == SRC_U8)
-    for (int i = tid; i < 768; i += TX_THREADS) sync->lut[i] = __ldg(p.lut + i);
   if (warp == TX_W_MMA) {
     tmem_alloc(&sync->tmem_base, TX_ACC * 128);
     tmem_relinquish();
@@ -168,6 +166,10 @@ stem_tx_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   // the pad rows/bytes of the 16-bit halo planes are never written by the converters: clear them once
   for (int i = tid; i < TX_ABUF * TX_A_STRIDE / 16; i += TX_THREADS)
     reinterpret_cast<uint4*>(abuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+  griddep_wait();       // up to here the CTA overlapped the previous kernel's tail; no global memory was read yet
+  if (tid < 16) { sync->scale[tid] = __ldg(p.scale + tid); sync->shift[tid] = __ldg(p.shift + tid); }
+  if (SRC == SRC_U8)
+    for (int i = tid; i < 768; i += TX_THREADS) sync->lut[i] = __ldg(p.lut + i);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -482,7 +484,7 @@ int stem_tx_forward(StemTxState* s, const void* x, int src_kind, const uint16_t*
   DRN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = std::min(p.total_pairs, sms);
   if (grid == 0) return DRNB200_OK;
-  kern<<<grid, TX_THREADS, smem, st>>>(s->map, s->map_y, p);
+  launch_chained(kern, grid, TX_THREADS, smem, st, s->map, s->map_y, p);
   DRN_CUDA(cudaGetLastError());
   return DRNB200_OK;
 }
