@@ -747,6 +747,39 @@ def test_data_writes_need_invalidate_or_verify_weights():
     assert torch.equal(m2.predict(xd), b)
 
 
+_CHAIN_SCRIPT = """
+import hashlib, sys
+sys.path[:0] = [%r, %r, %r]
+import torch
+from helpers import gate_case_cpu
+from oracle import recipe
+model, sd, masks = gate_case_cpu("drn_d_22", True, 21)
+model = model.cuda().eval(); model.set_masks(masks)
+x = recipe.make_frames(2, 128, 512, seed=77).cuda()
+h = hashlib.sha256()
+for _ in range(3):                       # back-to-back forwards: every kernel follows another one of the chain
+    final, seg = model(x)
+    h.update(model.predict(x).cpu().numpy().tobytes()); h.update(seg.cpu().numpy().tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_chained_launches_are_bit_identical_to_plain_stream_order():
+    """programmatic dependent launch: the persistent kernels start their prologue under the previous
+    kernel's tail and wait before their first global read; DRNB200_PDL=0 launches in plain stream order.  Same labels
+    and same low-res logits, bit for bit (the knob is read once per process, hence the two subprocesses)."""
+    import subprocess
+    import sys
+    script = _CHAIN_SCRIPT % (os.path.join(ROOT, "video-seg-model-compress_b200"), os.path.join(ROOT, "tests"), ROOT)
+    digests = []
+    for knob in ("1", "0"):
+        env = dict(os.environ, DRNB200_PDL=knob)
+        out = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][-1])
+    assert digests[0] == digests[1]
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_frames_on_another_device_and_data_parallel():
     """frames on cuda:1 while cuda:0 is the current device run on cuda:1 (per-device engines, device guard), and
