@@ -423,6 +423,31 @@ def host_ceiling(ctx, hx, label_bytes, seconds=0.4):
     return (reps * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9, reps * label_bytes / (b0.elapsed_time(b1) * 1e-3) / 1e9)
 
 
+def graph_replay_cases(model, x, iters=30):
+    """frames/s (wall clock, device synchronised on both sides) of DRNSeg.predict on ONE fixed device buffer: the eager
+    launch list vs one CUDA-graph replay (DRNSeg.enable_graphs).  Cases: the benchmark batch, one full-size frame (the
+    reference's test() loop feeds one frame per step) and one 304x304 frame (seg_video_old.py:127 resizes to 300x300)."""
+    N, _, H, W = x.shape
+    cases = [("batch%d_%dx%d" % (N, H, W), x), ("batch1_%dx%d" % (H, W), x[:1].contiguous()),
+             ("batch1_304x304", x[:1, :, :304, :304].contiguous())]
+    out = {}
+    for name, xin in cases:
+        row = {}
+        for mode in ("eager", "graphs"):
+            model.enable_graphs(mode == "graphs")
+            for _ in range(3):
+                model.predict(xin)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                model.predict(xin, static_output=True)
+            torch.cuda.synchronize()
+            row[mode] = round(xin.shape[0] * iters / (time.perf_counter() - t0), 1)
+        out[name] = row
+    model.enable_graphs(False)
+    return out
+
+
 def layer_table(eng, per_layer, B, H, W, pk):
     """per conv launch: live MACs, algorithmic bytes, achieved TFLOP/s and GB/s, and the fraction of whichever
     roofline (HBM at the measured copy bandwidth, tensor at the measured burst peak) bounds that launch"""
@@ -581,6 +606,7 @@ def main():
             other = {"act_dtype": odt, "value": world * B * args.steps / (o_ms * 1e-3), "unit": "frames/s",
                      "ms_per_step": o_ms / args.steps, "label_agreement_with_%s_path" % args.act: agree}
             model.set_act_dtype(args.act)
+        graphs = graph_replay_cases(model, x) if extras and H >= 304 and W >= 304 else None
 
     if rank == 0:
         frames = world * B * args.steps
@@ -632,6 +658,9 @@ def main():
                 "d2h_gbs_per_rank": [round(v, 2) for v in copy_rates["u8_d2h"]],
                 "note": "same pipeline fed with uint8 HWC frames; ToTensor+Normalize fused into the stem kernel"},
             "gpu_launches": launches,
+            "graph_replay": None if graphs is None else dict(
+                graphs, unit="frames/s", note="DRNSeg.predict on one fixed device buffer, wall clock: eager launch list "
+                "vs one CUDA-graph replay (enable_graphs); the headline numbers above use the eager list"),
             "host_numa": ctx.numa,
             "clocks": clocks,
             "roofline": {"bound": "tensor",

@@ -747,6 +747,57 @@ def test_data_writes_need_invalidate_or_verify_weights():
     assert torch.equal(m2.predict(xd), b)
 
 
+def test_graph_replay_matches_eager_and_follows_the_weights():
+    """DRNSeg.enable_graphs(): predict() replays one CUDA graph per input buffer — same kernels, same labels; a cache
+    rebuild (new masks, apply_masks-style in-place writes, invalidate) drops the graphs; uint8 ingest + FramePipeline
+    (fixed staging buffers, PIL-exact resize into a per-slot buffer) run through the graphs as well."""
+    model, sd, x = _gate_case("drn_d_22", 128, 256, 2, True, "fp16", seed=31)
+    x = x.to(dev())
+    buf = torch.empty_like(x)
+    frames = [x, x.flip(3).contiguous(), (x * 0.5 + 0.1).contiguous(), x.flip(2).contiguous()]
+    eager = []
+    for f in frames:
+        buf.copy_(f)
+        eager.append(model.predict(buf).clone())
+    assert not torch.equal(eager[0], eager[1])
+    model.enable_graphs()
+    eng = model.engine(dev())
+    for rep in range(2):
+        for f, ref in zip(frames, eager):
+            buf.copy_(f)
+            got = model.predict(buf)
+            assert torch.equal(got, ref)
+    assert len(eng._graphs) == 1                       # one input buffer, one graph
+    assert torch.equal(model.predict(frames[1]), eager[1])       # another buffer: its own graph (eager on first use)
+    assert torch.equal(model.predict(frames[1]), eager[1])
+    assert len(eng._graphs) == 2
+    # in-place weight write (what Pruner.apply_masks does): version counters move, graphs are dropped and rebuilt
+    w = model.state_dict()["layer.8.0.weight"]
+    w.mul_(-1.0)
+    buf.copy_(frames[0])
+    changed = model.predict(buf).clone()
+    assert len(eng._graphs) == 1
+    model.enable_graphs(False)
+    assert torch.equal(model.predict(buf), changed)
+    assert not torch.equal(changed, eager[0])
+    w.mul_(-1.0)
+    assert torch.equal(model.predict(buf), eager[0])
+    # uint8 frames through the streaming pipeline, with the resize: graphs on == graphs off
+    model.set_ingest([0.29, 0.33, 0.28], [0.18, 0.19, 0.18])
+    batches = [_u8_frames(2, 150, 280, seed=s) for s in range(5)]
+    outs = {}
+    for on in (False, True):
+        model.enable_graphs(on)
+        pipe = drnb200.FramePipeline(model, (2, 150, 280, 3), torch.uint8, resize_to=(96, 160), output="overlay")
+        outs[on] = [o.clone() for o in pipe.run(batches + batches)]
+        pipe.close()
+    assert len(outs[True]) == 10
+    for a, b in zip(outs[False], outs[True]):
+        assert torch.equal(a, b)
+    assert not torch.equal(outs[True][0], outs[True][1])
+    model.enable_graphs(False)
+
+
 _CHAIN_SCRIPT = """
 import hashlib, sys
 sys.path[:0] = [%r, %r, %r]

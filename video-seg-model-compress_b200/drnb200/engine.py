@@ -9,6 +9,7 @@ Data layout in HBM: activations NHWC 16-bit (bf16 or fp16, ``act_dtype``), one b
 drawn from a size-keyed pool; packed weights = live K-blocks only, in the swizzled shared-memory image.
 """
 import ctypes as C
+import collections
 import os
 
 import torch
@@ -441,6 +442,8 @@ class Engine:
         self.launches_per_forward = 0
         self.proj_in_k = os.environ.get("DRNB200_PROJ", "1") != "0"    # A/B knob: "0" keeps [conv1 | shortcut] everywhere
         self.last_ops = None
+        self._graphs = collections.OrderedDict()   # CUDA graphs of the label path, keyed by input buffer + shape
+        self._graph_pool = None
         self._build_graph()
 
     # ---- module tree -> op list ----------------------------------------------------------------
@@ -602,6 +605,7 @@ class Engine:
             self.stem_w = stem_w.to(device, torch.float32).contiguous()
             self._stem_version = ver
             self._drop_stem_plans()
+            rebuilt += 1
         seg = self.m.seg
         seg_w, seg_wver = _effective_weight(seg)
         hver = (seg_wver, seg.bias._version, self.act_dtype, str(device), stamp)
@@ -613,12 +617,16 @@ class Engine:
             self.seg_w = seg_w.to(device, torch.float32).reshape(seg.out_channels, -1).contiguous()
             self.seg_b = seg.bias.detach().to(device, torch.float32).contiguous()
             self.head_version = hver
+            rebuilt += 1
+        if rebuilt:
+            self._graphs.clear()       # captured launches point into the plans / weights that were just replaced
         return rebuilt
 
     def set_ingest(self, mean, std, bgr=False):
         """normalisation of uint8 frames (data_transforms.py:109-125: (x/255 - mean) / std per channel)"""
         self.ingest = (tuple(float(m) for m in mean), tuple(float(v) for v in std), bool(bgr))
         self._lut = None
+        self._graphs.clear()
 
     def _ingest_lut(self, device):
         if self._lut is None or self._lut[0] != (device, self.act_dtype):
@@ -682,24 +690,7 @@ class Engine:
         return dense + seg, live + seg, tile + seg
 
     # ---- forward ---------------------------------------------------------------------------------
-    def run(self, x, want_labels=True, want_logprob=False, want_seg=False, timings=None, taps=None):
-        """launch the whole path on the current stream.  `timings`, if a list, receives
-        (name, start_event, end_event) per launch group (CUDA events on the launching stream).
-        `taps`, if a dict, receives a float32 NCHW copy of every stored activation keyed by the state_dict prefix of
-        the conv that produced it (the keys of the oracle's taps; a fused [conv1 | downsample] launch yields both)."""
-        def timed(name):
-            return _Timed(name, timings)
-
-        tdt = torch.bfloat16 if self.act_dtype == ffi.BF16 else torch.float16
-
-        def tap(op_keys, buf, n, oh, ow, ch):
-            if taps is None:
-                return
-            t = buf[:n * oh * ow * ch].view(tdt).view(n, oh, ow, ch).float().permute(0, 3, 1, 2)
-            step = ch // len(op_keys)
-            for j, k in enumerate(op_keys):
-                taps[k] = t[:, j * step:(j + 1) * step].contiguous()
-
+    def _check_input(self, x):
         u8 = x.dtype == torch.uint8
         if u8:
             # frame ingest fused into the stem: uint8 HWC frames (cv2 / PIL order), normalisation via set_ingest()
@@ -723,10 +714,73 @@ class Engine:
         # seg_video_old.py:127)
         if W % 4 or H < 8 or W < 8:
             raise ffi.Drnb200Error("W must be a multiple of 4 and H, W >= 8 (got %dx%d)" % (H, W))
+        return u8, N, H, W
+
+    def run(self, x, want_labels=True, want_logprob=False, want_seg=False, timings=None, taps=None):
+        """launch the whole path on the current stream.  `timings`, if a list, receives
+        (name, start_event, end_event) per launch group (CUDA events on the launching stream).
+        `taps`, if a dict, receives a float32 NCHW copy of every stored activation keyed by the state_dict prefix of
+        the conv that produced it (the keys of the oracle's taps; a fused [conv1 | downsample] launch yields both)."""
+        def timed(name):
+            return _Timed(name, timings)
+
+        tdt = torch.bfloat16 if self.act_dtype == ffi.BF16 else torch.float16
+
+        def tap(op_keys, buf, n, oh, ow, ch):
+            if taps is None:
+                return
+            t = buf[:n * oh * ow * ch].view(tdt).view(n, oh, ow, ch).float().permute(0, 3, 1, 2)
+            step = ch // len(op_keys)
+            for j, k in enumerate(op_keys):
+                taps[k] = t[:, j * step:(j + 1) * step].contiguous()
+
+        u8, N, H, W = self._check_input(x)
         # every launch, allocation and stream query below must target the input's device, whatever the caller's
         # current device is (frames on cuda:1 while cuda:0 is current, DataParallel worker threads)
         with torch.cuda.device(x.device):
             return self._run(x, u8, N, H, W, want_labels, want_logprob, want_seg, timed, tap)
+
+    GRAPH_SLOTS = 8
+
+    def run_graphed(self, x, static_output=False):
+        """label map of `x` through a captured CUDA graph of the whole launch list (stem .. fused head).
+
+        The 22-39 launches of a forward cost the Python host 0.3-0.5 ms; at batch 8 of 1024x2048 frames the GPU needs
+        2.8 ms and hides that, at batch 1 (the reference's evaluation loop, semantic_seg.py test(): one frame per step)
+        or on small video frames it does not.  A graph replays the same kernels, tensor maps and programmatic
+        dependencies with one launch.  Graphs are keyed by the INPUT BUFFER (address, shape, dtype) because tensor maps
+        are kernel parameters: feed frames through a fixed set of device buffers (FramePipeline does).  First call with
+        a new key: one eager forward (creates the plans), then the capture; at most GRAPH_SLOTS graphs are kept (LRU),
+        all in one memory pool.  Any rebuild of the derived caches (weights, masks, BN, ingest) drops every graph.
+        static_output=True returns the graph's own label tensor, overwritten by the next replay of the same graph."""
+        u8, N, H, W = self._check_input(x)
+        if self.verify_weights or not x.is_contiguous():
+            return self.run(x, want_labels=True)[0]      # content fingerprints synchronise: no capture
+        with torch.cuda.device(x.device):
+            key = (x.data_ptr(), tuple(x.shape), x.dtype)
+            ent = self._graphs.get(key) if self.last_ops is not None else None
+            if ent is not None:
+                try:
+                    if self.refresh(x.device, self.last_ops):
+                        ent = None                       # refresh() dropped the graphs
+                except ProjFallback:
+                    ent = None
+            if ent is None:
+                labels = self.run(x, want_labels=True)[0]            # eager: plans, attributes, fallbacks
+                if self._graph_pool is None:
+                    self._graph_pool = torch.cuda.graph_pool_handle()
+                g = torch.cuda.CUDAGraph()
+                timed = lambda name: _Timed(name, None)
+                with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
+                    out = self._run(x, u8, N, H, W, True, False, False, timed, lambda *a: None)[0]
+                self._graphs[key] = (g, out)
+                while len(self._graphs) > self.GRAPH_SLOTS:
+                    self._graphs.popitem(last=False)
+                return labels                                        # the eager result of this very call
+            self._graphs.move_to_end(key)
+            g, out = ent
+            g.replay()
+            return out if static_output else out.clone()
 
     def _run(self, x, u8, N, H, W, want_labels, want_logprob, want_seg, timed, tap):
         x = x.contiguous()
@@ -826,6 +880,7 @@ class Engine:
         return labels, logprob, seg
 
     def close(self):
+        self._graphs.clear()
         lib = ffi.lib()
         for op in self.ops + (self.ops_proj or []):
             op.destroy_plans()

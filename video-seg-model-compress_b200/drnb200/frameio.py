@@ -89,9 +89,10 @@ def _resize_axis_tables(in_size, out_size, device):
     return t
 
 
-def resize_frames(frames, size):
+def resize_frames(frames, size, out=None):
     """uint8 CUDA frames [N,Hs,Ws,3] -> uint8 [N,h,w,3], bit-identical to `T.Resize((h, w))` on every PIL frame
-    (seg_video_old.py:125-128: Pillow's 8-bit BILINEAR resampler with its widened support when downscaling)."""
+    (seg_video_old.py:125-128: Pillow's 8-bit BILINEAR resampler with its widened support when downscaling).
+    `out`: optional destination (contiguous uint8 CUDA tensor [N,h,w,3] on the same device)."""
     if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4
             and frames.shape[3] == 3):
         raise ffi.Drnb200Error("resize_frames needs a uint8 CUDA tensor [N,H,W,3]; there is no CPU path")
@@ -100,7 +101,11 @@ def resize_frames(frames, size):
     N, Hs, Ws, _ = frames.shape
     dev = frames.device
     with torch.cuda.device(dev):
-        out = torch.empty((N, h, w, 3), dtype=torch.uint8, device=dev)
+        if out is None:
+            out = torch.empty((N, h, w, 3), dtype=torch.uint8, device=dev)
+        elif not (out.is_cuda and out.device == dev and out.dtype == torch.uint8 and out.is_contiguous()
+                  and tuple(out.shape) == (N, h, w, 3)):
+            raise ffi.Drnb200Error("resize_frames: `out` must be a contiguous uint8 tensor %s on %s" % ((N, h, w, 3), dev))
         tx, ty = _resize_axis_tables(Ws, w, dev), _resize_axis_tables(Hs, h, dev)
         tmp = torch.empty((N, Hs, w, 3), dtype=torch.uint8, device=dev) if tx is not None and ty is not None else None
         nul = (None, None, None, 0)

@@ -97,6 +97,7 @@ class DRNSeg(nn.Module):
         object.__setattr__(self, "_origin", weakref.ref(self))
         self._mask_dict = None
         self._ingest = None
+        self.use_graphs = False
 
     # ---- reference API ---------------------------------------------------------------------------
     def forward(self, x):
@@ -114,10 +115,21 @@ class DRNSeg(nn.Module):
 
     # ---- fast path / mask plumbing ---------------------------------------------------------------
     @torch.no_grad()
-    def predict(self, x):
+    def predict(self, x, static_output=False):
         """uint8 label map [N,H,W] == torch.max(model(x)[0], 1)[1] of the reference, without ever
-        writing the [N,classes,H,W] logits."""
+        writing the [N,classes,H,W] logits.  With ``use_graphs`` (see enable_graphs) the launch list is replayed as
+        one CUDA graph per input buffer; static_output=True then returns the graph's own output tensor."""
+        if self.use_graphs:
+            return self._eng(x).run_graphed(x, static_output=static_output)
         return self._eng(x).run(x, want_labels=True)[0]
+
+    def enable_graphs(self, on=True):
+        """replay predict() as a captured CUDA graph (Engine.run_graphed): one launch instead of 22-39 per forward.
+        Pays when the host, not the GPU, bounds the loop — one frame per step (the reference's test() loop) or small
+        video frames; feed the frames through a fixed set of device buffers (FramePipeline does), graphs are keyed by
+        the input buffer.  Same kernels, same results."""
+        self.use_graphs = bool(on)
+        return self
 
     def set_ingest(self, mean, std, bgr=False):
         """enable uint8 HWC frames [N,H,W,3] as input of forward()/predict(): ToTensorVideoImage + Normalize

@@ -58,6 +58,9 @@ class FramePipeline:
             self.copy_out = torch.cuda.Stream(device=self.dev)
             self.h_in = [frameio.HostBuffer(self.shape, dtype, host_mode) for _ in range(self.depth)]
             self.d_in = [torch.empty(self.shape, dtype=dtype, device=self.dev) for _ in range(self.depth)]
+            # resized frames live in per-slot buffers too: fixed addresses are what CUDA-graph replay keys on
+            self.d_rs = [torch.empty((B, h, w, 3), dtype=torch.uint8, device=self.dev) for _ in range(self.depth)] \
+                if self.resize_to is not None else None
             if output == "labels":
                 oshape, odt = (B, oh, ow), torch.uint8
             elif output == "overlay":
@@ -129,8 +132,11 @@ class FramePipeline:
         main.wait_event(self.returned[b])              # the device result of the batch that used this slot is on the host
         x = self.d_in[b]
         if self.resize_to is not None:
-            x = frameio.resize_frames(x, self.resize_to)
-        labels = self.model.predict(x)
+            x = frameio.resize_frames(x, self.resize_to, out=self.d_rs[b])
+        # with model.enable_graphs() the forward is one graph launch per staging buffer (d_in[b] is a fixed address); the
+        # graph's own label tensor is consumed by the copy-back / overlay / histogram right behind it on this stream
+        labels = self.model.predict(x, static_output=True) if getattr(self.model, "use_graphs", False) \
+            else self.model.predict(x)
         if self.output == "overlay":
             res = frameio.overlay(labels, x, self.alpha)
         elif self.output == "hist":
