@@ -116,8 +116,8 @@ typedef struct drnb200_conv_desc {
    * than 128 pixels); plan creation fails with DRNB200_E_ARG otherwise and the caller keeps the projection as a
    * separate launch. */
   int32_t proj_cin;
-  /* Accumulator orientation of the row-halo kernel (mode 5/6 below): 0 = chosen from the tile list (pixel-major when
-   * an output tile has <= 12 live K-blocks on average, i.e. when finishing a tile costs more than multiplying it),
+  /* Accumulator orientation of the row-halo kernel (mode 5/6 below): 0 = the library's choice (cout-major: the
+   * pixel-major flavour measured 20-45 % slower on every layer of the benchmark and is never picked on its own),
    * 1 = cout-major (TMEM lane = cout, staged shared-memory epilogue with TMA stores), 2 = pixel-major (TMEM lane =
    * pixel, register epilogue with 32-byte global accesses).  Results are identical; ignored by the other kernels. */
   int32_t acc_layout;
@@ -138,7 +138,8 @@ int  drnb200_conv_plan_impl(const drnb200_conv_plan* plan);
  * 1 = conv_tc MODE_P (pixels as M), 2 = conv_tc MODE_T with float32 output, 3 = conv_gather (im2col in smem),
  * 4 = conv_halo (shifted windows of one halo tile), 5 = conv_tc MODE_T ROW variant (3x3 stride 1, 64-channel K-blocks,
  * rows wider than 128 pixels: each input row loaded once, the three kx taps as shifted UMMA windows; the only kernel
- * that accepts proj_cin), 6 = the same with the pixel-major accumulator (acc_layout); -1 for direct plans */
+ * that accepts proj_cin), 6 = the same with the pixel-major accumulator (acc_layout), 7 = conv_ty (3x3 stride 1,
+ * 16 -> 16 channels: filter rows folded into the weight operand, each input row read once per kx); -1 for direct plans */
 int  drnb200_conv_plan_mode(const drnb200_conv_plan* plan);
 /* live multiply-accumulates of one forward (tile-list granularity) — the numerator of tensor-pipe
  * utilisation counted at block granularity; element-granularity MACs are computed by the host. */

@@ -124,7 +124,7 @@ def test_weight_packing_bit_exact(act, tiles):
 
 # ------------------------------------------------------------------------------------------------ (b)
 def _conv_case(N, H, W, cin, cout, k, stride, dil, relu, res, act, impl, density, seed, out_f32=True, acc_layout=0,
-               expect_mode=None):
+               expect_mode=None, live_taps=None):
     """one conv+BN(+res)(+ReLU) through the C ABI vs torch fp32 on the same 16-bit-representable operands"""
     lib = ffi.lib()
     g = torch.Generator().manual_seed(seed)
@@ -135,6 +135,11 @@ def _conv_case(N, H, W, cin, cout, k, stride, dil, relu, res, act, impl, density
     w = recipe.round_bf16(torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5)
     blocks = (torch.rand(cout // tile_o, cin // tile_ci, generator=g) < density).float()
     mask = torch.kron(blocks, torch.ones(tile_o, tile_ci))[:, :, None, None].expand(-1, -1, k, k).contiguous()
+    if live_taps is not None:                     # whole filter taps pruned (the tile list is per (cin block, ky, kx))
+        keep = torch.zeros(k, k)
+        for ky, kx in live_taps:
+            keep[ky, kx] = 1.0
+        mask = mask * keep
     w = w * mask
     scale = 0.5 + torch.rand(cout, generator=g)
     shift = 0.2 * torch.randn(cout, generator=g)
@@ -233,6 +238,75 @@ def test_conv_row_kernel_both_accumulator_layouts(case, layout, act):
         outs.append(_conv_case(N, H, W, cin, cout, 3, 1, dil, relu, res, act, ffi.IMPL_TCGEN05, dens,
                                seed=W + cin + cout, out_f32=False, acc_layout=lay, expect_mode=4 + lay))
     assert torch.equal(outs[0], outs[1])
+
+
+TY_CASES = [
+    # N  H    W   relu  live taps (None = all nine)          3x3 stride-1 16 -> 16 (DRN layer1), 16-bit output
+    (2, 24, 300, True, None),                                # three row tiles, the last one ragged (300 = 256 + 44)
+    (1, 19, 128, True, None),                                # H not a multiple of the 8-row tile, one full row tile
+    (1, 8, 40, False, None),                                 # narrower than a tile, no ReLU
+    (3, 9, 129, True, None),                                 # one pixel / one row in the second tiles
+    (1, 37, 260, True, [(0, 0), (1, 1), (2, 2), (0, 2)]),    # pruned taps (zero slots of the folded weight stack)
+    (1, 16, 136, True, [(2, 1)]),                            # a single live tap, and not the ky = 0 one that
+                                                             # initialises the accumulator columns
+    (2, 264, 640, True, None),                               # 330 tiles: two or three per CTA
+    (4, 400, 512, True, None),                               # 800 tiles: the halo ring and the accumulators wrap
+]
+
+
+@pytest.mark.parametrize("case", TY_CASES)
+@pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
+def test_conv_ty_layer1_kernel(case, act):
+    """conv_ty (plan mode 7: filter rows folded into the weight operand, 8 output rows x 16 couts as accumulator
+    columns) against torch fp32 on the same 16-bit operands, through the C ABI; guard bands checked by _conv_case"""
+    N, H, W, relu, taps = case
+    _conv_case(N, H, W, 16, 16, 3, 1, 1, relu, False, act, ffi.IMPL_TCGEN05, 1.0, seed=H * W, out_f32=False,
+               expect_mode=7, live_taps=taps)
+
+
+def test_conv_ty_many_launches_of_hbm_sized_batches():
+    """regression: with one barrier per halo slot, an MMA warp could ask for the NEXT fill of a slot whose current
+    fill was still in flight (TMA boxes complete out of order once the batch no longer fits in L2) and
+    mbarrier.try_wait.parity answered "done": 1-2 % of the launches of two 1024x2048 frames faulted.  300 launches of
+    one plan over two alternating buffer pairs (the tensor map is re-encoded at every switch) must all give the
+    first launch's bits."""
+    lib = ffi.lib()
+    d, N, H, W = dev(), 2, 1024, 2048
+    g = torch.Generator().manual_seed(7)
+    wd = (torch.randn(16, 16, 3, 3, generator=g) * 0.1).to(d)
+    md = torch.ones_like(wd)
+    rp = torch.empty(2, dtype=torch.int32, device=d)
+    kb = torch.empty(9, dtype=torch.int32, device=d)
+    nl = torch.zeros(1, dtype=torch.int32, device=d)
+    st = ffi.stream_ptr()
+    ffi.check(lib.drnb200_compact_mask(ffi.ptr(md), 16, 16, 3, 3, 16, 16, ffi.ptr(rp), ffi.ptr(kb), ffi.ptr(nl), st))
+    packed = torch.empty(9 * 256, dtype=torch.int16, device=d)
+    ffi.check(lib.drnb200_pack_weights(ffi.ptr(wd), ffi.ptr(md), 16, 16, 3, 3, 16, 16, ffi.ptr(rp), ffi.ptr(kb),
+                                       ffi.F16, ffi.ptr(packed), st))
+    desc = ffi.ConvDesc(N=N, H=H, W=W, Cin=16, Cout=16, ksize=3, stride=1, dilation=1, relu=1, has_residual=0,
+                        act_dtype=ffi.F16, out_f32=0, tile_o=16, tile_ci=16, impl=ffi.IMPL_TCGEN05, acc_layout=0)
+    plan = C.c_void_p()
+    sc, sh = torch.ones(16, device=d), torch.zeros(16, device=d)
+    ffi.check(lib.drnb200_conv_plan_create(C.byref(plan), C.byref(desc), ffi.ptr(rp), ffi.ptr(kb), ffi.ptr(packed),
+                                           ffi.ptr(sc), ffi.ptr(sh)))
+    assert lib.drnb200_conv_plan_mode(plan) == 7
+    xs = [torch.randn(N, H, W, 16, device=d, generator=torch.Generator(d).manual_seed(k)).half() for k in range(2)]
+    ys = [torch.empty(N, H, W, 16, device=d, dtype=torch.half) for _ in range(2)]
+    first = []
+    for k in range(2):
+        ffi.check(lib.drnb200_conv_forward(plan, ffi.ptr(xs[k]), None, ffi.ptr(ys[k]), st))
+        first.append(ys[k].clone())
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(xs[0][:1, :64].permute(0, 3, 1, 2).float(), wd.half().float(), None, 1, 1).relu()
+    assert (first[0][:1, :63].permute(0, 3, 1, 2).float() - ref[:, :, :63]).abs().max().item() <= 2.0 ** -9 * max(1.0, ref.max().item())
+    for r in range(300):
+        k = r % 2
+        ys[k].zero_()
+        ffi.check(lib.drnb200_conv_forward(plan, ffi.ptr(xs[k]), None, ffi.ptr(ys[k]), st))
+        if r % 50 >= 48:
+            assert torch.equal(ys[k], first[k]), r
+    torch.cuda.synchronize()
+    lib.drnb200_conv_plan_destroy(plan)
 
 
 @pytest.mark.parametrize("case", CONV_CASES[:9])

@@ -22,6 +22,8 @@ def main():
                 e = dict(os.environ); e.update(env)
                 out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--no-extras", "--steps", "20",
                                       "--warmup", "3", "--layers-out", f.name], env=e, capture_output=True, text=True)
+                if out.returncode != 0 or not out.stdout.strip():
+                    sys.exit("bench.py failed for variant %r (rc %d):\n%s" % (name, out.returncode, out.stderr[-3000:]))
                 line = json.loads(out.stdout.strip().splitlines()[-1])
                 res[name].append((line["value"], json.load(open(f.name))["per_layer_ms"]))
     names = [n for n, _ in variants]

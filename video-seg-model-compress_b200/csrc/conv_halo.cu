@@ -375,7 +375,13 @@ int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st) {
   const size_t fixed = 1024 + ((9u * p.w_tile_bytes + 1023u) & ~1023u) + sizeof(HSync);
   p.ring = (int)std::min<size_t>(H_MAX_RING, (kMaxSmem - fixed) / p.halo_bytes);
   if (p.ring < 2) { set_error("conv_halo: halo tile does not fit shared memory"); return DRNB200_E_ARG; }
-  p.n_mma = std::min(H_MMA_WARPS, p.ring);
+  // MMA warps take alternate tiles; tile i uses ring slot i % ring and accumulator set i % (H_ACC / H_MB).  Successive
+  // phases of one barrier must be awaited by the SAME warp: a second warp polling "next fill of slot b" while the
+  // current fill is still in flight is answered "done" by mbarrier.try_wait.parity (the barrier is two phases behind
+  // the question) — found in conv_ty.cu, where it faulted 1-2 % of the launches.  So n_mma divides both counts.
+  p.n_mma = 1;
+  for (int n = std::min(H_MMA_WARPS, p.ring); n > 1; --n)
+    if (p.ring % n == 0 && (H_ACC / H_MB) % n == 0) { p.n_mma = n; break; }
 
   static_assert(sizeof(HMapCache) <= sizeof(plan->gather_cache), "halo cache storage too small");
   HMapCache* cache = reinterpret_cast<HMapCache*>(plan->gather_cache);

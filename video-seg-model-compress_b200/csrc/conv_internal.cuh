@@ -72,6 +72,9 @@ constexpr int TC_MODE_GATHER = 3;
 bool conv_halo_supported(const drnb200_conv_desc& d);       // stride-1 3x3, Cin,Cout <= 64 (conv_halo.cu)
 int conv_halo_launch(drnb200_conv_plan* plan, cudaStream_t st);
 constexpr int TC_MODE_HALO = 4;
+bool conv_ty_supported(const drnb200_conv_desc& d);         // 3x3 stride-1 16 -> 16 (conv_ty.cu: Toeplitz along y)
+int conv_ty_launch(drnb200_conv_plan* plan, cudaStream_t st);
+constexpr int TC_MODE_TY = 7;
 // Toeplitz-weight stem (stem_tx.cu)
 struct StemTxState;
 int stem_tx_create(StemTxState** out, const float* w_oihw, int act_dtype, cudaStream_t st);

@@ -75,7 +75,10 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
   plan->impl = 0;
   // narrow stride-1 3x3 layers (Cin, Cout <= 64): shifted-window halo kernel (no im2col copy);
   // 16-channel stride-2 layers: im2col-gather kernel; everything else: per-tap TMA implicit GEMM
-  if (d.impl != DRNB200_IMPL_DIRECT && conv_halo_supported(d)) {
+  if (d.impl != DRNB200_IMPL_DIRECT && conv_ty_supported(d)) {
+    plan->impl = DRNB200_IMPL_TCGEN05;
+    plan->tc_mode = TC_MODE_TY;
+  } else if (d.impl != DRNB200_IMPL_DIRECT && conv_halo_supported(d)) {
     plan->impl = DRNB200_IMPL_TCGEN05;
     plan->tc_mode = TC_MODE_HALO;
   } else if (d.impl != DRNB200_IMPL_DIRECT && conv_gather_supported(d)) {
@@ -120,6 +123,7 @@ extern "C" int drnb200_conv_forward(drnb200_conv_plan* plan, const void* x_nhwc,
   plan->p.y = y_nhwc;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->impl != DRNB200_IMPL_TCGEN05) return conv_direct_launch(plan, st);
+  if (plan->tc_mode == TC_MODE_TY) return conv_ty_launch(plan, st);
   if (plan->tc_mode == TC_MODE_HALO) return conv_halo_launch(plan, st);
   return plan->tc_mode == TC_MODE_GATHER ? conv_gather_launch(plan, st) : conv_tc_launch(plan, st);
 }
