@@ -264,6 +264,29 @@ def test_conv_ty_layer1_kernel(case, act):
                expect_mode=7, live_taps=taps)
 
 
+S2_CASES = [
+    # N  H    W   relu  live taps (None = all nine)          3x3 stride-2 16 -> 32 (DRN layer2), 16-bit output, even W
+    (2, 24, 300, True, None),                                # 150 output pixels: a ragged second row tile
+    (1, 19, 256, True, None),                                # odd H (10 output rows: 2.5 row tiles), one full tile
+    (1, 8, 40, False, None),                                 # narrower than a tile, no ReLU
+    (3, 18, 258, True, None),                                # one output pixel / one output row in the second tiles
+    (1, 37, 520, True, [(0, 0), (1, 1), (2, 2), (0, 2)]),    # pruned taps (zero slots of the weight stacks)
+    (1, 16, 272, True, [(2, 0)]),                            # a single live tap, not one of the accumulate-off ones
+    (1, 16, 272, True, [(1, 0)]),                            # only the tap whose MMA initialises the columns
+    (2, 528, 1280, True, None),                              # 1320 tiles: slots, accumulators and barriers wrap
+]
+
+
+@pytest.mark.parametrize("case", S2_CASES)
+@pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
+def test_conv_s2_layer2_kernel(case, act):
+    """conv_s2 (plan mode 8: stride 2 through pixel-pair operand rows, filter rows folded into the weight operand)
+    against torch fp32 on the same 16-bit operands, through the C ABI; guard bands checked by _conv_case"""
+    N, H, W, relu, taps = case
+    _conv_case(N, H, W, 16, 32, 3, 2, 1, relu, False, act, ffi.IMPL_TCGEN05, 1.0, seed=H * W + 1, out_f32=False,
+               expect_mode=8, live_taps=taps)
+
+
 def test_conv_ty_many_launches_of_hbm_sized_batches():
     """regression: with one barrier per halo slot, an MMA warp could ask for the NEXT fill of a slot whose current
     fill was still in flight (TMA boxes complete out of order once the batch no longer fits in L2) and

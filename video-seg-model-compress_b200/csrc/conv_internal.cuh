@@ -75,6 +75,9 @@ constexpr int TC_MODE_HALO = 4;
 bool conv_ty_supported(const drnb200_conv_desc& d);         // 3x3 stride-1 16 -> 16 (conv_ty.cu: Toeplitz along y)
 int conv_ty_launch(drnb200_conv_plan* plan, cudaStream_t st);
 constexpr int TC_MODE_TY = 7;
+bool conv_s2_supported(const drnb200_conv_desc& d);         // 3x3 stride-2 16 -> 32 (conv_s2.cu: pixel-pair operand rows)
+int conv_s2_launch(drnb200_conv_plan* plan, cudaStream_t st);
+constexpr int TC_MODE_S2 = 8;
 // Toeplitz-weight stem (stem_tx.cu)
 struct StemTxState;
 int stem_tx_create(StemTxState** out, const float* w_oihw, int act_dtype, cudaStream_t st);

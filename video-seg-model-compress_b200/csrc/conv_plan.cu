@@ -78,6 +78,9 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
   if (d.impl != DRNB200_IMPL_DIRECT && conv_ty_supported(d)) {
     plan->impl = DRNB200_IMPL_TCGEN05;
     plan->tc_mode = TC_MODE_TY;
+  } else if (d.impl != DRNB200_IMPL_DIRECT && conv_s2_supported(d)) {
+    plan->impl = DRNB200_IMPL_TCGEN05;
+    plan->tc_mode = TC_MODE_S2;
   } else if (d.impl != DRNB200_IMPL_DIRECT && conv_halo_supported(d)) {
     plan->impl = DRNB200_IMPL_TCGEN05;
     plan->tc_mode = TC_MODE_HALO;
@@ -124,6 +127,7 @@ extern "C" int drnb200_conv_forward(drnb200_conv_plan* plan, const void* x_nhwc,
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->impl != DRNB200_IMPL_TCGEN05) return conv_direct_launch(plan, st);
   if (plan->tc_mode == TC_MODE_TY) return conv_ty_launch(plan, st);
+  if (plan->tc_mode == TC_MODE_S2) return conv_s2_launch(plan, st);
   if (plan->tc_mode == TC_MODE_HALO) return conv_halo_launch(plan, st);
   return plan->tc_mode == TC_MODE_GATHER ? conv_gather_launch(plan, st) : conv_tc_launch(plan, st);
 }
