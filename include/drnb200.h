@@ -139,7 +139,7 @@ int  drnb200_conv_plan_impl(const drnb200_conv_plan* plan);
  * 4 = conv_halo (shifted windows of one halo tile), 5 = conv_tc MODE_T ROW variant (3x3 stride 1, 64-channel K-blocks,
  * rows wider than 128 pixels: each input row loaded once, the three kx taps as shifted UMMA windows; the only kernel
  * that accepts proj_cin), 6 = the same with the pixel-major accumulator (acc_layout), 7 = conv_ty (3x3 stride 1,
- * 16 -> 16 channels: filter rows folded into the weight operand, each input row read once per kx), 8 = conv_s2 (3x3
+ * 16 -> 16 channels, even W: pixel-pair operand rows, filter rows folded into the weight operand), 8 = conv_s2 (3x3
  * stride 2, 16 -> 32 channels, even W: the input viewed as pixel pairs so that the stride is part of the operand layout,
  * no im2col copy); -1 for direct plans */
 int  drnb200_conv_plan_mode(const drnb200_conv_plan* plan);

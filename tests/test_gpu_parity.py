@@ -242,10 +242,11 @@ def test_conv_row_kernel_both_accumulator_layouts(case, layout, act):
 
 TY_CASES = [
     # N  H    W   relu  live taps (None = all nine)          3x3 stride-1 16 -> 16 (DRN layer1), 16-bit output
-    (2, 24, 300, True, None),                                # three row tiles, the last one ragged (300 = 256 + 44)
-    (1, 19, 128, True, None),                                # H not a multiple of the 8-row tile, one full row tile
+    (2, 24, 300, True, None),                                # two row tiles, the second one ragged (300 = 256 + 44)
+    (1, 19, 256, True, None),                                # H not a multiple of the 8-row tile, one full row tile
+    (1, 11, 770, True, None),                                # four row tiles, one pixel pair in the last
     (1, 8, 40, False, None),                                 # narrower than a tile, no ReLU
-    (3, 9, 129, True, None),                                 # one pixel / one row in the second tiles
+    (3, 9, 258, True, None),                                 # one pixel pair / one row in the second tiles
     (1, 37, 260, True, [(0, 0), (1, 1), (2, 2), (0, 2)]),    # pruned taps (zero slots of the folded weight stack)
     (1, 16, 136, True, [(2, 1)]),                            # a single live tap, and not the ky = 0 one that
                                                              # initialises the accumulator columns
@@ -257,11 +258,18 @@ TY_CASES = [
 @pytest.mark.parametrize("case", TY_CASES)
 @pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
 def test_conv_ty_layer1_kernel(case, act):
-    """conv_ty (plan mode 7: filter rows folded into the weight operand, 8 output rows x 16 couts as accumulator
-    columns) against torch fp32 on the same 16-bit operands, through the C ABI; guard bands checked by _conv_case"""
+    """conv_ty (plan mode 7: pixel-pair operand rows, filter rows folded into the weight operand, 8 output rows x 2
+    pixels x 16 couts as accumulator columns) against torch fp32 on the same 16-bit operands, through the C ABI; guard
+    bands checked by _conv_case"""
     N, H, W, relu, taps = case
     _conv_case(N, H, W, 16, 16, 3, 1, 1, relu, False, act, ffi.IMPL_TCGEN05, 1.0, seed=H * W, out_f32=False,
                expect_mode=7, live_taps=taps)
+
+
+def test_conv_ty_and_s2_leave_odd_widths_to_the_older_kernels():
+    """the pixel-pair view needs an even W: odd widths run on conv_halo (mode 4) / conv_gather (mode 3) as before"""
+    _conv_case(1, 9, 129, 16, 16, 3, 1, 1, True, False, ffi.F16, ffi.IMPL_TCGEN05, 1.0, seed=3, out_f32=False, expect_mode=4)
+    _conv_case(1, 9, 129, 16, 32, 3, 2, 1, True, False, ffi.F16, ffi.IMPL_TCGEN05, 1.0, seed=4, out_f32=False, expect_mode=3)
 
 
 S2_CASES = [
