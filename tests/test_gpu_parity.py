@@ -295,6 +295,30 @@ def test_conv_s2_layer2_kernel(case, act):
                expect_mode=8, live_taps=taps)
 
 
+YS_CASES = [
+    # N  H    W   relu  res    live taps (None = all nine)      3x3 stride-1 64 -> 64 (DRN layer3 blocks), 16-bit output
+    (2, 24, 300, True, True, None),                           # three row tiles, the last one ragged (300 = 256 + 44)
+    (1, 19, 128, True, False, None),                          # H not a multiple of the 8-row segment
+    (1, 8, 40, False, True, None),                            # narrower than a tile, residual without ReLU
+    (3, 9, 129, True, True, None),                            # one pixel / one row in the second tiles
+    (1, 37, 260, True, True, [(0, 0), (1, 1), (2, 2), (0, 2)]),   # pruned taps (zero blocks of the weight stacks)
+    (1, 16, 136, True, False, [(2, 1)]),                      # a single live tap, not the accumulate-off one
+    (2, 136, 520, True, True, None),                          # 170 items: more than one per CTA, rings and slots wrap
+    (4, 264, 512, True, False, None),                         # 528 items
+]
+
+
+@pytest.mark.parametrize("case", YS_CASES)
+@pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
+def test_conv_ys_layer3_kernel(case, act):
+    """conv_ys (plan mode 9: input rows streamed through single-row slots, filter rows folded into the weight
+    operand, one TMEM slot per output row of the 8-row segment) against torch fp32 on the same 16-bit operands,
+    through the C ABI; guard bands checked by _conv_case"""
+    N, H, W, relu, res, taps = case
+    _conv_case(N, H, W, 64, 64, 3, 1, 1, relu, res, act, ffi.IMPL_TCGEN05, 1.0, seed=H * W + 2, out_f32=False,
+               expect_mode=9, live_taps=taps)
+
+
 def test_conv_ty_many_launches_of_hbm_sized_batches():
     """regression: with one barrier per halo slot, an MMA warp could ask for the NEXT fill of a slot whose current
     fill was still in flight (TMA boxes complete out of order once the batch no longer fits in L2) and

@@ -58,7 +58,7 @@ struct drnb200_conv_plan {
   const void* tmap_y_ptr;
   const void* tmap_r_ptr;
   std::vector<int32_t> h_row_ptr;
-  alignas(64) unsigned char gather_cache[256];   // GMapCache of conv_gather.cu (halo tensor map)
+  alignas(64) unsigned char gather_cache[512];   // GMapCache of conv_gather.cu (halo tensor map)
   bool gather_cache_init = false;
 };
 
@@ -78,6 +78,9 @@ constexpr int TC_MODE_TY = 7;
 bool conv_s2_supported(const drnb200_conv_desc& d);         // 3x3 stride-2 16 -> 32 (conv_s2.cu: pixel-pair operand rows)
 int conv_s2_launch(drnb200_conv_plan* plan, cudaStream_t st);
 constexpr int TC_MODE_S2 = 8;
+bool conv_ys_supported(const drnb200_conv_desc& d);         // 3x3 stride-1 64 -> 64 (+ residual) (conv_ys.cu: streamed input rows)
+int conv_ys_launch(drnb200_conv_plan* plan, cudaStream_t st);
+constexpr int TC_MODE_YS = 9;
 // Toeplitz-weight stem (stem_tx.cu)
 struct StemTxState;
 int stem_tx_create(StemTxState** out, const float* w_oihw, int act_dtype, cudaStream_t st);
