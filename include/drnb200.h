@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DRNB200_VERSION 109
+#define DRNB200_VERSION 110
 
 /* error codes */
 #define DRNB200_OK          0

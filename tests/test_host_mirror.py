@@ -257,7 +257,10 @@ def test_c_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), name
     lib = ffi.lib()
-    assert lib.drnb200_version() == 109
+    assert lib.drnb200_version() == 110
+    # the timing probes that make results invalid (DRNB200_DBG, `make EXTRA=-DDRNB200_DIAG`) must not be in the
+    # library that ships: the built .so travels to the GPU box as it is
+    assert b"DRNB200_DBG" not in open(ffi.LIB_PATH, "rb").read(), "libdrnb200.so is a -DDRNB200_DIAG build: make clean && make"
     # argument validation happens before any CUDA call, so it is testable here
     assert lib.drnb200_compact_mask(None, 8, 8, 3, 3, 8, 8, None, None, None, None) == -1
     assert b"null pointer" in lib.drnb200_last_error()
