@@ -454,7 +454,7 @@ def layer_table(eng, per_layer, B, H, W, pk):
     import drnb200
     lib = drnb200.ffi.lib()
     KERNELS = {0: "conv_tc<T>", 1: "conv_tc<P>", 2: "conv_tc<T,f32>", 3: "conv_gather", 4: "conv_halo",
-               5: "conv_tc<T,ROW>", 6: "conv_tc<T,ROW,PIX>", 7: "conv_ty", 8: "conv_s2", 9: "conv_ys", -1: "conv_direct"}
+               5: "conv_tc<T,ROW>", 6: "conv_tc<T,ROW,PIX>", 7: "conv_ty", 8: "conv_s2", 9: "conv_ys", 10: "conv_y2", -1: "conv_direct"}
     layers = []
     shapes = {-1: (H, W)}
     ops = eng.last_ops or eng.ops

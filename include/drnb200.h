@@ -142,7 +142,8 @@ int  drnb200_conv_plan_impl(const drnb200_conv_plan* plan);
  * 16 -> 16 channels, even W: pixel-pair operand rows, filter rows folded into the weight operand), 8 = conv_s2 (3x3
  * stride 2, 16 -> 32 channels, even W: the input viewed as pixel pairs so that the stride is part of the operand layout,
  * no im2col copy), 9 = conv_ys (3x3 stride 1, 64 -> 64 channels (+ residual), dilation 1: input rows streamed through a
- * ring of single-row slots, filter rows folded into the weight operand); -1 for direct plans */
+ * ring of single-row slots, filter rows folded into the weight operand), 10 = conv_y2 (3x3 stride 2, 32 -> 128 channels,
+ * even W, tightly packed input: the same streaming over pixel-pair rows); -1 for direct plans */
 int  drnb200_conv_plan_mode(const drnb200_conv_plan* plan);
 /* live multiply-accumulates of one forward (tile-list granularity) — the numerator of tensor-pipe
  * utilisation counted at block granularity; element-granularity MACs are computed by the host. */

@@ -319,6 +319,29 @@ def test_conv_ys_layer3_kernel(case, act):
                expect_mode=9, live_taps=taps)
 
 
+Y2_CASES = [
+    # N  H    W   relu  live taps (None = all nine)          3x3 stride-2 32 -> 128 (DRN block 3.0 conv1 + downsample)
+    (2, 24, 300, True, None),                                # 150 output pixels: a ragged second row tile
+    (1, 19, 256, True, None),                                # odd H (10 output rows: 2.5 segments), one full tile
+    (1, 8, 40, False, None),                                 # narrower than a tile, no ReLU
+    (3, 18, 258, True, None),                                # one output pixel / one output row in the second tiles
+    (1, 37, 520, True, [(0, 0), (1, 1), (2, 2), (0, 2)]),    # pruned taps (zero blocks of the weight stacks)
+    (1, 16, 272, True, [(2, 0)]),                            # a single live tap, not one of the accumulate-off ones
+    (1, 16, 272, True, [(1, 0)]),                            # only the tap whose MMA initialises the columns
+    (2, 528, 1280, True, None),                              # 1320 items: ring, slots and barriers wrap
+]
+
+
+@pytest.mark.parametrize("case", Y2_CASES)
+@pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
+def test_conv_y2_block30_kernel(case, act):
+    """conv_y2 (plan mode 10: stride 2 through streamed pixel-pair rows, filter rows folded into the weight operand,
+    staged TMA stores) against torch fp32 on the same 16-bit operands, through the C ABI"""
+    N, H, W, relu, taps = case
+    _conv_case(N, H, W, 32, 128, 3, 2, 1, relu, False, act, ffi.IMPL_TCGEN05, 1.0, seed=H * W + 3, out_f32=False,
+               expect_mode=10, live_taps=taps)
+
+
 def test_conv_ty_many_launches_of_hbm_sized_batches():
     """regression: with one barrier per halo slot, an MMA warp could ask for the NEXT fill of a slot whose current
     fill was still in flight (TMA boxes complete out of order once the batch no longer fits in L2) and

@@ -81,6 +81,9 @@ constexpr int TC_MODE_S2 = 8;
 bool conv_ys_supported(const drnb200_conv_desc& d);         // 3x3 stride-1 64 -> 64 (+ residual) (conv_ys.cu: streamed input rows)
 int conv_ys_launch(drnb200_conv_plan* plan, cudaStream_t st);
 constexpr int TC_MODE_YS = 9;
+bool conv_y2_supported(const drnb200_conv_desc& d);         // 3x3 stride-2 32 -> 128 (conv_y2.cu: streamed pixel-pair rows)
+int conv_y2_launch(drnb200_conv_plan* plan, cudaStream_t st);
+constexpr int TC_MODE_Y2 = 10;
 // Toeplitz-weight stem (stem_tx.cu)
 struct StemTxState;
 int stem_tx_create(StemTxState** out, const float* w_oihw, int act_dtype, cudaStream_t st);

@@ -81,6 +81,9 @@ extern "C" int drnb200_conv_plan_create(drnb200_conv_plan** out, const drnb200_c
   } else if (d.impl != DRNB200_IMPL_DIRECT && conv_s2_supported(d)) {
     plan->impl = DRNB200_IMPL_TCGEN05;
     plan->tc_mode = TC_MODE_S2;
+  } else if (d.impl != DRNB200_IMPL_DIRECT && conv_y2_supported(d)) {
+    plan->impl = DRNB200_IMPL_TCGEN05;
+    plan->tc_mode = TC_MODE_Y2;
   } else if (d.impl != DRNB200_IMPL_DIRECT && conv_ys_supported(d)) {
     plan->impl = DRNB200_IMPL_TCGEN05;
     plan->tc_mode = TC_MODE_YS;
@@ -132,6 +135,7 @@ extern "C" int drnb200_conv_forward(drnb200_conv_plan* plan, const void* x_nhwc,
   if (plan->tc_mode == TC_MODE_TY) return conv_ty_launch(plan, st);
   if (plan->tc_mode == TC_MODE_S2) return conv_s2_launch(plan, st);
   if (plan->tc_mode == TC_MODE_YS) return conv_ys_launch(plan, st);
+  if (plan->tc_mode == TC_MODE_Y2) return conv_y2_launch(plan, st);
   if (plan->tc_mode == TC_MODE_HALO) return conv_halo_launch(plan, st);
   return plan->tc_mode == TC_MODE_GATHER ? conv_gather_launch(plan, st) : conv_tc_launch(plan, st);
 }
