@@ -1207,6 +1207,46 @@ def test_uint8_ingest_is_bit_identical_to_normalised_float_frames(act, hw):
     assert rel_err(seg_u8.cpu(), ref_seg) <= (LOGIT_RTOL if act == "fp16" else 2 * LOGIT_RTOL)
 
 
+@pytest.mark.parametrize("act", [ffi.BF16, ffi.F16])
+@pytest.mark.parametrize("shape", [(2, 150, 72), (1, 128, 16), (1, 261, 304), (3, 40, 20)])
+def test_stem_kernels_vs_fp32(shape, act):
+    """the 7x7 stem in isolation, through the C ABI: the tcgen05 Toeplitz kernel (drnb200_stem_plan_*: input and weights
+    rounded to the activation dtype, fp32 accumulation, BN affine + ReLU, one output rounding) and the CUDA-core fp32
+    cross-check (drnb200_stem_forward: no operand rounding) against torch conv2d; tile edges in both directions (rows
+    beyond a 128-row tile, a single 8-column tile, widths that are not a multiple of the 16-column tile pair)"""
+    lib = ffi.lib()
+    N, H, W = shape
+    d = dev()
+    g = torch.Generator().manual_seed(H * W + N)
+    tdt = torch.bfloat16 if act == ffi.BF16 else torch.float16
+    x = torch.randn(N, 3, H, W, generator=g)
+    w = torch.randn(16, 3, 7, 7, generator=g) * (2.0 / 147) ** 0.5
+    scale = 0.5 + torch.rand(16, generator=g)
+    shift = 0.2 * torch.randn(16, generator=g)
+    aff = lambda t: (t * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu()      # noqa: E731
+    ref16 = aff(torch.nn.functional.conv2d(x.to(tdt).float(), w.to(tdt).float(), None, 1, 3))
+    ref32 = aff(torch.nn.functional.conv2d(x, w, None, 1, 3))
+    xd, wd, sc, sh = x.to(d), w.to(d), scale.to(d), shift.to(d)
+    st = ffi.stream_ptr()
+    G = 4096
+    flat = torch.full((N * H * W * 16 + 2 * G,), float("nan"), dtype=tdt, device=d)
+    y = flat[G:G + N * H * W * 16].view(N, H, W, 16)
+    plan = C.c_void_p()
+    ffi.check(lib.drnb200_stem_plan_create(C.byref(plan), ffi.ptr(wd), ffi.ptr(sc), ffi.ptr(sh), N, H, W, 16, act, st))
+    ffi.check(lib.drnb200_stem_plan_forward(plan, ffi.ptr(xd), ffi.ptr(y), st))
+    torch.cuda.synchronize()
+    lib.drnb200_stem_plan_destroy(plan)
+    assert bool(torch.isnan(flat[:G]).all()) and bool(torch.isnan(flat[-G:]).all())      # nothing written outside y
+    got = y.float().permute(0, 3, 1, 2).cpu()
+    tol = 2.0 ** -8 if act == ffi.BF16 else 2.0 ** -10                                   # one output rounding
+    assert (got - ref16).abs().max().item() <= tol * max(1.0, ref16.abs().max().item())
+    y2 = torch.empty(N, H, W, 16, dtype=tdt, device=d)
+    ffi.check(lib.drnb200_stem_forward(ffi.ptr(xd), ffi.ptr(wd), ffi.ptr(sc), ffi.ptr(sh), N, H, W, 16, act, ffi.ptr(y2), st))
+    torch.cuda.synchronize()
+    got2 = y2.float().permute(0, 3, 1, 2).cpu()
+    assert (got2 - ref32).abs().max().item() <= tol * max(1.0, ref32.abs().max().item())
+
+
 def test_uint8_ingest_validation():
     model, sd, _ = _gate_case("drn_d_22", 64, 128, 1, False, "fp16", seed=22)
     frames = torch.zeros(1, 64, 128, 3, dtype=torch.uint8, device=dev())
