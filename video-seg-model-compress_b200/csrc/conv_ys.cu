@@ -221,16 +221,14 @@ conv_ys_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     // this group's rows as one sequence k = 0, 1, ...: item k / 4, output row grp + 2 * (k % 4).  The residual of row
     // k + 1 (128 B per pixel) is requested before row k is finished, so that its latency hides behind a whole row.
     constexpr int RPI = YS_SEG / YS_EPI_GROUPS;              // rows per item and group
-    int sx0 = 0, sy = 0, sn = 0, sx0_n = 0, sy_n = 0, sn_n = 0;   // store coordinates of the current / next row
-    auto locate = [&](int k, int& yo, size_t& pix, int& cx, int& cy, int& cn) -> bool {   // false: outside the image
+    int sx0 = 0, sy = 0, sn = 0, sx0_n = 0, sy_n = 0, sn_n = 0;   // TMA coordinates of the current / next row
+    auto locate = [&](int k, int& yo, int& cx, int& cy, int& cn) -> bool {   // false: past this CTA's last item
       const int t = blockIdx.x + (k / RPI) * gridDim.x;
       yo = grp + YS_EPI_GROUPS * (k % RPI);
       if (t >= p.total_tiles) return false;
       const YsTile c = ys_decode(p, t);
-      const int ox = c.ox0 + m, oy = c.oy0 + yo;
-      cx = c.ox0; cy = oy; cn = c.n;
-      pix = ((size_t)c.n * p.H + oy) * p.W + ox;
-      return ox < p.W && oy < p.H;
+      cx = c.ox0; cy = c.oy0 + yo; cn = c.n;
+      return true;
     };
     uint32_t rv[4][8];
     // residual row of output row (cx, cy, cn): tensor {64, W, H, N} over channels [res_coff, res_coff + 64) of the
@@ -244,16 +242,14 @@ conv_ys_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       }
     };
     int yo = 0, yo_n = 0;
-    size_t pix = 0, pix_n = 0;
-    bool ok = locate(0, yo, pix, sx0, sy, sn), ok_n = false;
-    (void)ok; (void)ok_n; (void)pix; (void)pix_n;
-    if (HAS_RES && issuer) request(blockIdx.x < (unsigned)p.total_tiles, sx0, sy, sn);
+    const bool any = locate(0, yo, sx0, sy, sn);              // grid <= items: every CTA has at least one
+    if (HAS_RES && issuer) request(any, sx0, sy, sn);
     const int n_rows = ((p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * RPI;
 #pragma unroll 1
     for (int k = 0; k < n_rows; ++k) {
       const uint32_t item = (uint32_t)(k / RPI);
       {
-        ok_n = locate(k + 1, yo_n, pix_n, sx0_n, sy_n, sn_n);
+        locate(k + 1, yo_n, sx0_n, sy_n, sn_n);
         if (HAS_RES) {
           mbar_wait(&sync->r_full[grp], (uint32_t)k & 1u);
 #pragma unroll
@@ -315,7 +311,7 @@ conv_ys_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           bulk_commit_group();
         }
       }
-      yo = yo_n; pix = pix_n; ok = ok_n; sx0 = sx0_n; sy = sy_n; sn = sn_n;
+      yo = yo_n; sx0 = sx0_n; sy = sy_n; sn = sn_n;
     }
     if (issuer) bulk_wait_group<0>();
   }
